@@ -1,0 +1,537 @@
+// CPU checker ("twin") of the batched GPU algorithms.  TEST INFRASTRUCTURE - never linked into the product.
+//
+// This is NOT the reference's algorithm (that is oracle/ppopt_oracle.py, which follows PPOPT call by call
+// with an external LP solver).  It is a sequential statement of what the CUDA kernels compute per candidate
+// (same program reduction, same pivoting rules, same thresholds) so that
+//   (1) the batched algorithm's DECISIONS can be validated against the reference's golden status bytes on
+//       a machine without a GPU, and
+//   (2) GPU parity tests can compare the kernels with a second, independent implementation.
+// Reference semantics being reproduced per candidate:
+//   rank       is_full_rank                   /root/reference/src/ppopt/utils/constraint_utilities.py:222-236
+//   feasible   MPLP_Program.check_feasibility /root/reference/src/ppopt/mplp_program.py:411-444
+//   optimal    check_optimality               /root/reference/src/ppopt/mpqp_program.py:203-322, mplp_program.py:446-569
+//   region     gen_cr_from_active_set(_1d)    /root/reference/src/ppopt/utils/mpqp_utils.py:89-320
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../ppopt_b200/csrc/host_math.hpp"
+#include "../ppopt_b200/csrc/tolerances.h"
+
+using ppgpu::ReducedProgram;
+using ppgpu::vec;
+
+namespace {
+
+struct Lp {
+    int nr = 0, nc = 0;        // rows, nonbasic columns (1..nc); column 0 = rhs
+    std::vector<double> T;     // nr x (nc+1)
+    std::vector<int> rowflag;  // 0 dead, 1 live (basic slack >= 0), 2 pending equality
+    std::vector<int> colkind;  // index 1..nc: 0 dead, 1 free, 2 slack
+    std::vector<int> bvar, nbvar;
+    int js = 0;                // column of the margin variable s
+    long pivots = 0;
+    double& at(int r, int c) { return T[(size_t)r * (nc + 1) + c]; }
+};
+
+struct LpResult { int code; double beta; };
+
+void pivot(Lp& lp, int r, int j, double dir, bool row_stays, std::vector<double>& alpha, bool have_obj) {
+    const int nc = lp.nc;
+    std::vector<double> P(nc + 1);
+    for (int c = 0; c <= nc; ++c) P[c] = lp.at(r, c);
+    const double piv = dir * P[j];
+    const double inv = 1.0 / piv;
+    P[j] = 1.0;
+    for (int i = 0; i < lp.nr; ++i) {
+        if (i == r || lp.rowflag[i] == 0) continue;
+        const double f = dir * lp.at(i, j) * inv;
+        lp.at(i, j) = 0.0;
+        for (int c = 0; c <= nc; ++c) lp.at(i, c) = std::fma(-f, P[c], lp.at(i, c));
+    }
+    if (have_obj) {
+        const double f = dir * alpha[j] * inv;
+        alpha[j] = 0.0;
+        for (int c = 0; c <= nc; ++c) alpha[c] = std::fma(-f, P[c], alpha[c]);
+    }
+    if (row_stays) {
+        for (int c = 0; c <= nc; ++c) lp.at(r, c) = P[c] * inv;
+    }
+    lp.pivots++;
+}
+
+// maximise s; returns early once beta >= thr (strict: beta > thr)
+LpResult lp_maxmin(Lp& lp, double thr, bool strict) {
+    const int nc = lp.nc, nr = lp.nr;
+    std::vector<double> alpha(nc + 1, 0.0);
+    // Phase A: eliminate pending equality rows
+    for (int e = 0; e < nr; ++e) {
+        if (lp.rowflag[e] != 2) continue;
+        int j = -1; double best = 0.0;
+        for (int c = 1; c <= nc; ++c)
+            if (lp.colkind[c] == 1 && c != lp.js && std::fabs(lp.at(e, c)) > best) { best = std::fabs(lp.at(e, c)); j = c; }
+        if (j < 0 || best < PPG_PIV_TOL) {
+            if (std::fabs(lp.at(e, 0)) > PPG_FEAS_TOL) return {PPG_LP_INFEAS_EQ, -INFINITY};
+            lp.rowflag[e] = 0;
+            continue;
+        }
+        pivot(lp, e, j, 1.0, false, alpha, false);
+        lp.rowflag[e] = 0;
+        lp.colkind[j] = 0;
+    }
+    // Phase B: s enters at the row of minimum rhs
+    int r0 = -1; double mn = INFINITY;
+    for (int i = 0; i < nr; ++i)
+        if (lp.rowflag[i] == 1 && lp.at(i, 0) < mn) { mn = lp.at(i, 0); r0 = i; }
+    if (r0 < 0) return {PPG_LP_UNBOUNDED, INFINITY};
+    {
+        // objective row = new row r0 after the pivot: alpha = P'/piv with P'[js] = 1
+        const double piv = lp.at(r0, lp.js);
+        for (int c = 0; c <= nc; ++c) alpha[c] = lp.at(r0, c) / piv;
+        alpha[lp.js] = 1.0 / piv;
+        std::vector<double> dummy;
+        pivot(lp, r0, lp.js, 1.0, false, dummy, false);
+        lp.rowflag[r0] = 0;
+        lp.colkind[lp.js] = 2;
+        lp.nbvar[lp.js] = nc + 1 + r0;
+    }
+    int degen = 0; bool bland = false;
+    const long cap = 50L * (nr + nc) + 200;
+    for (long it = 0;; ++it) {
+        const double beta = alpha[0];
+        if (strict ? (beta > thr) : (beta >= thr)) return {PPG_LP_EARLY, beta};
+        if (it > cap) return {PPG_LP_ITERLIM, beta};
+        // pricing
+        int j = -1; double best = PPG_OPT_TOL; int bestvar = 1 << 30;
+        for (int c = 1; c <= nc; ++c) {
+            double score = -1.0;
+            if (lp.colkind[c] == 1) score = std::fabs(alpha[c]);
+            else if (lp.colkind[c] == 2) score = -alpha[c];
+            if (score <= PPG_OPT_TOL) continue;
+            if (bland) { if (lp.nbvar[c] < bestvar) { bestvar = lp.nbvar[c]; j = c; } }
+            else if (score > best) { best = score; j = c; }
+        }
+        if (j < 0) return {PPG_LP_OPTIMAL, beta};
+        const double dir = (lp.colkind[j] == 1 && alpha[j] > 0.0) ? -1.0 : 1.0;
+        // ratio test (Harris two-pass; Bland: smallest basic variable among exact-min ties)
+        double tmax = INFINITY;
+        for (int i = 0; i < nr; ++i) {
+            if (lp.rowflag[i] != 1) continue;
+            const double a = dir * lp.at(i, j);
+            if (a > PPG_PIV_TOL) {
+                const double rhs = std::fmax(lp.at(i, 0), 0.0);
+                tmax = std::fmin(tmax, (rhs + PPG_HARRIS) / a);
+            }
+        }
+        if (tmax == INFINITY) return {PPG_LP_UNBOUNDED, INFINITY};
+        int r = -1; double bpiv = 0.0; int bvar = 1 << 30;
+        for (int i = 0; i < nr; ++i) {
+            if (lp.rowflag[i] != 1) continue;
+            const double a = dir * lp.at(i, j);
+            if (a > PPG_PIV_TOL) {
+                const double rhs = std::fmax(lp.at(i, 0), 0.0);
+                if (rhs / a <= tmax) {
+                    if (bland) { if (lp.bvar[i] < bvar) { bvar = lp.bvar[i]; r = i; } }
+                    else if (a > bpiv) { bpiv = a; r = i; }
+                }
+            }
+        }
+        const double step = std::fmax(lp.at(r, 0), 0.0) / (dir * lp.at(r, j));
+        if (step <= PPG_DEGEN_STEP) { if (++degen > PPG_BLAND_AFTER) bland = true; } else degen = 0;
+        const bool entering_free = lp.colkind[j] == 1;
+        const int enter_var = lp.nbvar[j];
+        pivot(lp, r, j, dir, !entering_free, alpha, true);
+        lp.colkind[j] = 2;
+        lp.nbvar[j] = lp.bvar[r];
+        if (entering_free) lp.rowflag[r] = 0; else lp.bvar[r] = enter_var;
+        for (int i = 0; i < nr; ++i)
+            if (lp.rowflag[i] == 1 && lp.at(i, 0) < 0.0 && lp.at(i, 0) > -1e-9) lp.at(i, 0) = 0.0;
+    }
+}
+
+void lp_init(Lp& lp, int nr, int nfreecols) {
+    lp.nr = nr; lp.nc = nfreecols + 1; lp.js = nfreecols + 1;
+    lp.T.assign((size_t)nr * (lp.nc + 1), 0.0);
+    lp.rowflag.assign(nr, 1);
+    lp.colkind.assign(lp.nc + 1, 1);
+    lp.colkind[0] = 0;
+    lp.bvar.resize(nr); lp.nbvar.resize(lp.nc + 1);
+    for (int i = 0; i < nr; ++i) lp.bvar[i] = lp.nc + 1 + i;
+    for (int c = 0; c <= lp.nc; ++c) lp.nbvar[c] = c;
+    lp.pivots = 0;
+}
+
+struct Twin {
+    ReducedProgram P;
+    long lp_pivots = 0;
+};
+
+void active_list(const ReducedProgram& P, const uint64_t* mask, std::vector<int>& act) {
+    act.clear();
+    for (int i = 0; i < P.mi; ++i)
+        if ((mask[i >> 6] >> (i & 63)) & 1ull) act.push_back(i);
+}
+
+// K1: column-pivoted Householder QR of the n' x k' matrix whose columns are the active reduced rows
+int rank_check(const ReducedProgram& P, const std::vector<int>& act, double* ratio_out) {
+    const int k = (int)act.size(), np = P.np;
+    if (ratio_out) *ratio_out = 1.0;
+    if (k == 0) return 1;
+    if (k > np) { if (ratio_out) *ratio_out = 0.0; return 0; }
+    std::vector<double> M((size_t)np * k);
+    for (int j = 0; j < k; ++j) for (int i = 0; i < np; ++i) M[(size_t)i * k + j] = P.At[(size_t)act[j] * np + i];
+    std::vector<char> done(k, 0);
+    double first = 0.0, minratio = 1.0;
+    for (int s = 0; s < k; ++s) {
+        int pj = -1; double best = -1.0;
+        for (int j = 0; j < k; ++j) {
+            if (done[j]) continue;
+            double nn = 0.0;
+            for (int i = s; i < np; ++i) nn += M[(size_t)i * k + j] * M[(size_t)i * k + j];
+            if (nn > best) { best = nn; pj = j; }
+        }
+        const double rss = std::sqrt(best);
+        if (s == 0) first = rss;
+        if (first == 0.0) { if (ratio_out) *ratio_out = 0.0; return 0; }
+        const double ratio = rss / first;
+        minratio = std::fmin(minratio, ratio);
+        if (ratio <= PPG_RANK_TOL) { if (ratio_out) *ratio_out = minratio; return 0; }
+        done[pj] = 1;
+        // Householder on column pj, rows s..np-1
+        std::vector<double> v(np, 0.0);
+        for (int i = s; i < np; ++i) v[i] = M[(size_t)i * k + pj];
+        const double alpha = v[s] >= 0 ? -rss : rss;
+        v[s] -= alpha;
+        double vtv = 0.0;
+        for (int i = s; i < np; ++i) vtv += v[i] * v[i];
+        if (vtv > 0.0) {
+            for (int j = 0; j < k; ++j) {
+                if (done[j]) continue;
+                double d = 0.0;
+                for (int i = s; i < np; ++i) d += v[i] * M[(size_t)i * k + j];
+                d = 2.0 * d / vtv;
+                for (int i = s; i < np; ++i) M[(size_t)i * k + j] -= d * v[i];
+            }
+        }
+    }
+    if (ratio_out) *ratio_out = minratio;
+    return 1;
+}
+
+// K2: feasibility LP  max s : rows + s <= rhs, active rows equalities
+int feas_check(Twin& tw, const std::vector<int>& act, double* margin_out, int* code_out) {
+    const ReducedProgram& P = tw.P;
+    Lp lp;
+    lp_init(lp, P.R0, P.nfree);
+    const int dc = P.nfree + 2;
+    for (int i = 0; i < P.R0; ++i)
+        for (int c = 0; c < dc; ++c) lp.at(i, c) = P.T0[(size_t)i * dc + c];
+    for (int a : act) { lp.rowflag[a] = 2; lp.at(a, lp.js) = 0.0; }
+    LpResult res = lp_maxmin(lp, -PPG_FEAS_TOL, false);
+    tw.lp_pivots += lp.pivots;
+    if (margin_out) *margin_out = res.beta;
+    if (code_out) *code_out = res.code;
+    if (res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED) return 1;
+    if (res.code == PPG_LP_OPTIMAL) return res.beta >= -PPG_FEAS_TOL;
+    return 0;
+}
+
+// rows a.theta <= f, layout [f | a(t)], returns: 0 not optimal, 1 screen passed; radius in *rad
+// zero-row rule and normalisation as in gen_cr_from_active_set (mpqp_utils.py:123-126)
+int polytope_test(Twin& tw, std::vector<double>& rows, int nrows, int t, double thr, bool strict, double* rad,
+                  std::vector<int>* nonzero_flags) {
+    std::vector<int> keep;
+    bool zero_violation = false;
+    for (int i = 0; i < nrows; ++i) {
+        double* r = &rows[(size_t)i * (t + 1)];
+        double mx = 0.0, nn = 0.0;
+        for (int c = 1; c <= t; ++c) { mx = std::fmax(mx, std::fabs(r[c])); nn += r[c] * r[c]; }
+        const bool nz = !(mx <= PPG_ZERO_ROW);
+        if (nonzero_flags) (*nonzero_flags)[i] = nz;
+        if (!nz) { if (r[0] < -PPG_FEAS_TOL) zero_violation = true; continue; }
+        const double inv = 1.0 / std::sqrt(nn);
+        for (int c = 0; c <= t; ++c) r[c] *= inv;
+        keep.push_back(i);
+    }
+    if (rad) *rad = -INFINITY;
+    if (zero_violation) return 0;
+    if (t == 1) {
+        double mn = -INFINITY, mxv = INFINITY;
+        for (int i : keep) {
+            const double* r = &rows[(size_t)i * 2];
+            if (r[1] > 0) mxv = std::fmin(mxv, r[0] / r[1]); else mn = std::fmax(mn, r[0] / r[1]);
+        }
+        if (rad) *rad = 0.5 * (mxv - mn);
+        return (mn + thr <= mxv) ? 1 : 0;  // thr = PPG_WIDTH_1D (final) or half of it (screen)
+    }
+    Lp lp;
+    lp_init(lp, (int)keep.size(), t);
+    for (size_t ii = 0; ii < keep.size(); ++ii) {
+        const double* r = &rows[(size_t)keep[ii] * (t + 1)];
+        lp.at((int)ii, 0) = r[0];
+        for (int c = 1; c <= t; ++c) lp.at((int)ii, c) = r[c];
+        lp.at((int)ii, lp.js) = 1.0;
+    }
+    LpResult res = lp_maxmin(lp, thr, strict);
+    tw.lp_pivots += lp.pivots;
+    if (rad) *rad = res.beta;
+    if (res.code == PPG_LP_EARLY) return 1;
+    if (res.code == PPG_LP_OPTIMAL) return strict ? (res.beta > thr) : (res.beta >= thr);
+    return 0;  // unbounded Chebyshev LP: the reference's solver returns None -> not full dimensional
+}
+
+// K3 (Gram/Cholesky) + K4: theta-space rows from the precomputed Gram, then the polytope test
+int kkt_cheb_gram(Twin& tw, const std::vector<int>& act, double* rad) {
+    const ReducedProgram& P = tw.P;
+    const int k = (int)act.size(), t = P.t, mi = P.mi;
+    std::vector<double> S((size_t)k * k), L((size_t)k * (t + 1));
+    for (int a = 0; a < k; ++a) for (int b2 = 0; b2 < k; ++b2) S[(size_t)a * k + b2] = P.G[(size_t)act[a] * mi + act[b2]];
+    if (k > 0 && !ppgpu::cholesky_lower(S, k)) { if (rad) *rad = -INFINITY; return -1; }
+    // Lambda = -S^-1 V_act
+    for (int col = 0; col <= t; ++col) {
+        std::vector<double> y(k);
+        for (int i = 0; i < k; ++i) {
+            double s = -P.V[(size_t)act[i] * (t + 1) + col];
+            for (int j = 0; j < i; ++j) s -= S[(size_t)i * k + j] * y[j];
+            y[i] = s / S[(size_t)i * k + i];
+        }
+        for (int i = k - 1; i >= 0; --i) {
+            double s = y[i];
+            for (int j = i + 1; j < k; ++j) s -= S[(size_t)j * k + i] * L[(size_t)j * (t + 1) + col];
+            L[(size_t)i * (t + 1) + col] = s / S[(size_t)i * k + i];
+        }
+    }
+    std::vector<double> rows((size_t)P.R0 * (t + 1));
+    std::vector<int> pos(mi, -1);
+    for (int a = 0; a < k; ++a) pos[act[a]] = a;
+    for (int i = 0; i < mi; ++i) {
+        double* r = &rows[(size_t)i * (t + 1)];
+        if (pos[i] >= 0) {
+            r[0] = L[(size_t)pos[i] * (t + 1)];
+            for (int c = 1; c <= t; ++c) r[c] = -L[(size_t)pos[i] * (t + 1) + c];
+        } else {
+            for (int c = 0; c <= t; ++c) {
+                double s = P.V[(size_t)i * (t + 1) + c];
+                for (int a = 0; a < k; ++a) s += P.G[(size_t)i * mi + act[a]] * L[(size_t)a * (t + 1) + c];
+                r[c] = c == 0 ? s : -s;
+            }
+        }
+    }
+    for (int i = 0; i < P.q; ++i) {
+        double* r = &rows[(size_t)(mi + i) * (t + 1)];
+        r[0] = P.bt[i];
+        for (int c = 1; c <= t; ++c) r[c] = P.At_theta[(size_t)i * t + c - 1];
+    }
+    const double thr = t == 1 ? 0.5 * PPG_WIDTH_1D : PPG_RADIUS_SCREEN;
+    return polytope_test(tw, rows, P.R0, t, thr, false, rad, nullptr);
+}
+
+// dense LU with partial pivoting on the KKT matrix of mpqp_program.py:182-190; laws (n+k) x (t+1), [const | theta]
+bool kkt_lu(const ReducedProgram& P, const std::vector<int>& act_full, std::vector<double>& laws) {
+    const int n = P.n, t = P.t, k = (int)act_full.size(), N = n + k, nrhs = t + 1;
+    std::vector<double> M((size_t)N * (N + nrhs), 0.0);
+    const int ld = N + nrhs;
+    for (int a = 0; a < k; ++a) {
+        const int row = act_full[a];
+        for (int j = 0; j < n; ++j) M[(size_t)a * ld + j] = P.A[(size_t)row * n + j];
+        M[(size_t)a * ld + N] = P.b[row];
+        for (int c = 0; c < t; ++c) M[(size_t)a * ld + N + 1 + c] = P.F[(size_t)row * t + c];
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) M[(size_t)(k + i) * ld + j] = P.Q[(size_t)i * n + j];
+        for (int a = 0; a < k; ++a) M[(size_t)(k + i) * ld + n + a] = P.A[(size_t)act_full[a] * n + i];
+        M[(size_t)(k + i) * ld + N] = -P.c[i];
+        for (int c = 0; c < t; ++c) M[(size_t)(k + i) * ld + N + 1 + c] = -P.H[(size_t)i * t + c];
+    }
+    for (int col = 0; col < N; ++col) {
+        int p = col; double best = std::fabs(M[(size_t)col * ld + col]);
+        for (int i = col + 1; i < N; ++i)
+            if (std::fabs(M[(size_t)i * ld + col]) > best) { best = std::fabs(M[(size_t)i * ld + col]); p = i; }
+        if (best == 0.0 || !std::isfinite(best)) return false;
+        if (p != col) for (int c = 0; c < ld; ++c) std::swap(M[(size_t)p * ld + c], M[(size_t)col * ld + c]);
+        const double inv = 1.0 / M[(size_t)col * ld + col];
+        for (int i = col + 1; i < N; ++i) {
+            const double f = M[(size_t)i * ld + col] * inv;
+            if (f == 0.0) continue;
+            for (int c = col + 1; c < ld; ++c) M[(size_t)i * ld + c] -= f * M[(size_t)col * ld + c];
+        }
+    }
+    laws.assign((size_t)N * nrhs, 0.0);
+    for (int c = 0; c < nrhs; ++c)
+        for (int i = N - 1; i >= 0; --i) {
+            double s = M[(size_t)i * ld + N + c];
+            for (int j = i + 1; j < N; ++j) s -= M[(size_t)i * ld + j] * laws[(size_t)j * nrhs + c];
+            laws[(size_t)i * nrhs + c] = s / M[(size_t)i * ld + i];
+        }
+    return true;
+}
+
+// Region emission for one active set; rows in the reference order [lambda rows, inactive rows, Theta rows].
+// flags: bit0 nonzero row, bit1 non-redundant, bit2 exact duplicate of an earlier kept row.
+// info[0]=region(0/1) info[1]=radius (t>1) or half width (t==1) info[2]=min bound info[3]=max bound
+int emit_region(Twin& tw, const std::vector<int>& act, double* laws_out, double* rows_out, int32_t* flags_out,
+                double* info, double* margins_out = nullptr) {
+    const ReducedProgram& P = tw.P;
+    const int n = P.n, t = P.t, ne = P.ne, m = P.m, kk = (int)act.size();
+    std::vector<int> act_full;
+    for (int i = 0; i < ne; ++i) act_full.push_back(i);
+    for (int a : act) act_full.push_back(ne + a);
+    const int k = (int)act_full.size();
+    std::vector<double> laws;
+    info[0] = 0; info[1] = -INFINITY; info[2] = -INFINITY; info[3] = INFINITY;
+    if (!kkt_lu(P, act_full, laws)) return -1;
+    for (size_t i = 0; i < laws.size(); ++i) laws_out[i] = laws[i];
+    const int nrhs = t + 1, R0 = P.R0;
+    std::vector<double> rows((size_t)R0 * nrhs);
+    std::vector<char> is_act(m, 0);
+    for (int a : act_full) is_act[a] = 1;
+    int ri = 0;
+    for (int a = 0; a < kk; ++a, ++ri) {  // -C theta <= d for the activated inequalities
+        const double* l = &laws[(size_t)(n + ne + a) * nrhs];
+        rows[(size_t)ri * nrhs] = l[0];
+        for (int c = 1; c <= t; ++c) rows[(size_t)ri * nrhs + c] = -l[c];
+    }
+    for (int i = 0; i < m; ++i) {
+        if (is_act[i]) continue;
+        for (int c = 0; c <= t; ++c) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s += P.A[(size_t)i * n + j] * laws[(size_t)j * nrhs + c];
+            rows[(size_t)ri * nrhs + c] = c == 0 ? P.b[i] - s : s - P.F[(size_t)i * t + c - 1];
+        }
+        ++ri;
+    }
+    for (int i = 0; i < P.q; ++i, ++ri) {
+        rows[(size_t)ri * nrhs] = P.bt[i];
+        for (int c = 1; c <= t; ++c) rows[(size_t)ri * nrhs + c] = P.At_theta[(size_t)i * t + c - 1];
+    }
+    std::vector<int> nz(R0, 0);
+    double rad = 0.0;
+    const int ok = polytope_test(tw, rows, R0, t, t == 1 ? PPG_WIDTH_1D : PPG_RADIUS, t != 1, &rad, &nz);
+    for (int i = 0; i < R0; ++i) flags_out[i] = nz[i] ? 1 : 0;
+    for (size_t i = 0; i < rows.size(); ++i) rows_out[i] = rows[i];
+    info[1] = rad;
+    if (!ok) return 0;
+    std::vector<int> keep;
+    for (int i = 0; i < R0; ++i) if (nz[i]) keep.push_back(i);
+    if (t == 1) {
+        double mn = -INFINITY, mx = INFINITY;
+        for (int i : keep) {
+            const double* r = &rows[(size_t)i * 2];
+            if (r[1] > 0) mx = std::fmin(mx, r[0] / r[1]); else mn = std::fmax(mn, r[0] / r[1]);
+        }
+        info[2] = mn; info[3] = mx;
+        for (int i : keep) {
+            const double* r = &rows[(size_t)i * 2];
+            const double v = r[0] / r[1];
+            if (mn <= v && v <= mx) flags_out[i] |= 2;
+        }
+    } else {
+        for (size_t a = 0; a < keep.size(); ++a) {  // redundancy LP: row `a` forced to equality
+            Lp lp;
+            lp_init(lp, (int)keep.size(), t);
+            for (size_t ii = 0; ii < keep.size(); ++ii) {
+                const double* r = &rows[(size_t)keep[ii] * nrhs];
+                lp.at((int)ii, 0) = r[0];
+                for (int c = 1; c <= t; ++c) lp.at((int)ii, c) = r[c];
+                lp.at((int)ii, lp.js) = ii == a ? 0.0 : 1.0;
+            }
+            lp.rowflag[a] = 2;
+            LpResult res = lp_maxmin(lp, margins_out ? 1e30 : -PPG_REDUND_TOL, false);
+            tw.lp_pivots += lp.pivots;
+            if (margins_out) margins_out[keep[a]] = res.beta;
+            bool feas = res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED ||
+                        (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_REDUND_TOL);
+            if (feas) flags_out[keep[a]] |= 2;
+        }
+        for (int i = 0; i < R0; ++i) {  // exact duplicates among the kept rows (numpy.unique semantics)
+            if ((flags_out[i] & 3) != 3) continue;
+            for (int j = 0; j < i; ++j) {
+                if ((flags_out[j] & 3) != 3 || (flags_out[j] & 4)) continue;
+                bool same = true;  // value equality (so -0.0 == 0.0), as numpy.unique compares
+                for (int c = 0; c < nrhs && same; ++c) same = rows[(size_t)i * nrhs + c] == rows[(size_t)j * nrhs + c];
+                if (same) { flags_out[i] |= 4; break; }
+            }
+        }
+    }
+    info[0] = 1;
+    return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* twin_create(int n, int t, int m, int q, int ne, int is_qp, const double* A, const double* b, const double* F,
+                  const double* A_t, const double* b_t, const double* Q, const double* c, const double* H) {
+    Twin* tw = new Twin();
+    if (!ppgpu::reduce_program(n, t, m, q, ne, is_qp, A, b, F, A_t, b_t, Q, c, H, tw->P)) { delete tw; return nullptr; }
+    return tw;
+}
+void twin_destroy(void* h) { delete (Twin*)h; }
+int twin_words(void* h) { return ((Twin*)h)->P.W; }
+int twin_use_gram(void* h) { return ((Twin*)h)->P.use_gram; }
+long twin_pivots(void* h) { return ((Twin*)h)->lp_pivots; }
+
+// status byte per candidate; aux (n x 3): [rank ratio, feasibility margin, radius]
+// screen_only=1: stop at the Gram screen (bit PPG_ST_OPT); 0: also run the LU emission test (bit PPG_ST_REGION)
+void twin_eval(void* h, const uint64_t* masks, long ncand, int final_level_lp, uint8_t* status, double* aux) {
+    Twin& tw = *(Twin*)h;
+    const ReducedProgram& P = tw.P;
+    std::vector<int> act;
+    std::vector<double> laws((size_t)(P.n + P.m) * (P.t + 1)), rows((size_t)P.R0 * (P.t + 1));
+    std::vector<int32_t> flags(P.R0);
+    for (long ci = 0; ci < ncand; ++ci) {
+        active_list(P, masks + ci * P.W, act);
+        uint8_t st = 0;
+        double ratio = 1.0, margin = 0.0, rad = -INFINITY;
+        if (rank_check(P, act, &ratio)) st |= PPG_ST_RANK;
+        if (ratio > PPG_RANK_BORDER_LO && ratio < PPG_RANK_BORDER_HI) st |= PPG_ST_BORDER;
+        if (st & PPG_ST_RANK) {
+            int code = 0;
+            if (feas_check(tw, act, &margin, &code)) st |= PPG_ST_FEAS;
+            if (code == PPG_LP_ITERLIM) st |= PPG_ST_NUMERIC;
+        }
+        if (st & PPG_ST_FEAS) {
+            int screen = 0;
+            if (P.is_qp && P.use_gram) {
+                screen = kkt_cheb_gram(tw, act, &rad);
+                if (screen < 0) { st |= PPG_ST_NUMERIC; screen = 0; }
+            } else if (P.is_qp) {
+                screen = 1;
+            } else {
+                screen = (P.ne + (int)act.size() == P.n) ? 1 : 0;  // mplp_program.py:472-473
+            }
+            if (screen) {
+                st |= PPG_ST_OPT;
+                double info[4];
+                int r = emit_region(tw, act, laws.data(), rows.data(), flags.data(), info);
+                if (r < 0) st |= PPG_ST_NUMERIC;
+                if (r > 0) st |= PPG_ST_REGION;
+                rad = info[1];
+            }
+        }
+        (void)final_level_lp;
+        status[ci] = st;
+        if (aux) { aux[ci * 3] = ratio; aux[ci * 3 + 1] = margin; aux[ci * 3 + 2] = rad; }
+    }
+}
+
+int twin_emit(void* h, const uint64_t* mask, double* laws_out, double* rows_out, int32_t* flags_out, double* info) {
+    Twin& tw = *(Twin*)h;
+    std::vector<int> act;
+    active_list(tw.P, mask, act);
+    return emit_region(tw, act, laws_out, rows_out, flags_out, info);
+}
+
+// debug variant: runs every redundancy LP to optimality and reports its margin s*
+int twin_emit_margins(void* h, const uint64_t* mask, double* laws_out, double* rows_out, int32_t* flags_out,
+                      double* info, double* margins_out) {
+    Twin& tw = *(Twin*)h;
+    std::vector<int> act;
+    active_list(tw.P, mask, act);
+    return emit_region(tw, act, laws_out, rows_out, flags_out, info, margins_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""ctypes binding of oracle/_build/libtwin.so (the CPU checker of the batched algorithms).  TEST INFRASTRUCTURE."""
+import ctypes
+import os
+import subprocess
+
+import numpy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(HERE, '_build', 'libtwin.so')
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_PATH):
+            subprocess.check_call(['make', '-C', HERE])
+        l = ctypes.CDLL(_PATH)
+        l.twin_create.restype = ctypes.c_void_p
+        l.twin_create.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 8
+        l.twin_destroy.argtypes = [ctypes.c_void_p]
+        l.twin_words.argtypes = [ctypes.c_void_p]
+        l.twin_use_gram.argtypes = [ctypes.c_void_p]
+        l.twin_pivots.argtypes = [ctypes.c_void_p]
+        l.twin_pivots.restype = ctypes.c_long
+        l.twin_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        l.twin_emit.argtypes = [ctypes.c_void_p] * 6
+        l.twin_emit_margins.argtypes = [ctypes.c_void_p] * 7
+        _lib = l
+    return _lib
+
+
+def _c(a):
+    return numpy.ascontiguousarray(numpy.asarray(a, dtype=numpy.float64))
+
+
+class Twin:
+    def __init__(self, A, b, F, A_t, b_t, Q, c, H, n_eq, is_qp):
+        A, F = _c(A), _c(F)
+        self.n, self.t, self.m = A.shape[1], F.shape[1], A.shape[0]
+        A_t = _c(A_t).reshape(-1, self.t)
+        self.q, self.n_eq, self.is_qp = A_t.shape[0], int(n_eq), bool(is_qp)
+        Q = _c(Q) if is_qp else numpy.zeros((self.n, self.n))
+        self._keep = [A, _c(b).ravel(), F, A_t, _c(b_t).ravel(), Q, _c(c).ravel(), _c(H)]
+        self.h = lib().twin_create(self.n, self.t, self.m, self.q, self.n_eq, int(self.is_qp), *[x.ctypes.data for x in self._keep])
+        if not self.h:
+            raise RuntimeError('twin_create failed')
+        self.W = lib().twin_words(self.h)
+        self.R0 = self.m - self.n_eq + self.q
+
+    @classmethod
+    def from_npz(cls, path):
+        g = numpy.load(path)
+        is_qp = str(g['kind']) == 'qp'
+        return cls(g['A'], g['b'], g['F'], g['A_t'], g['b_t'], g['Q'] if is_qp else None, g['c'], g['H'], int(g['n_eq']), is_qp)
+
+    def masks(self, active_sets):
+        out = numpy.zeros((len(active_sets), self.W), dtype=numpy.uint64)
+        for ci, aset in enumerate(active_sets):
+            for idx in aset:
+                i = int(idx) - self.n_eq
+                if i >= 0:
+                    out[ci, i >> 6] |= numpy.uint64(1) << numpy.uint64(i & 63)
+        return out
+
+    def eval(self, masks, aux=False):
+        masks = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(-1, self.W)
+        st = numpy.zeros(masks.shape[0], dtype=numpy.uint8)
+        ax = numpy.zeros((masks.shape[0], 3))
+        lib().twin_eval(self.h, masks.ctypes.data, masks.shape[0], 0, st.ctypes.data, ax.ctypes.data)
+        return (st, ax) if aux else st
+
+    def emit(self, mask, margins=False):
+        mask = numpy.ascontiguousarray(mask).view(numpy.uint64).reshape(self.W)
+        k = self.n_eq + int(sum(bin(int(w)).count('1') for w in mask))
+        laws = numpy.zeros((self.n + k, self.t + 1))
+        rows = numpy.zeros((self.R0, self.t + 1))
+        flags = numpy.zeros(self.R0, dtype=numpy.int32)
+        info = numpy.zeros(4)
+        if margins:
+            mg = numpy.full(self.R0, numpy.nan)
+            rc = lib().twin_emit_margins(self.h, mask.ctypes.data, laws.ctypes.data, rows.ctypes.data, flags.ctypes.data,
+                                         info.ctypes.data, mg.ctypes.data)
+            return rc, laws, rows, flags, info, mg
+        rc = lib().twin_emit(self.h, mask.ctypes.data, laws.ctypes.data, rows.ctypes.data, flags.ctypes.data, info.ctypes.data)
+        return rc, laws, rows, flags, info
+
+    def pivots(self):
+        return lib().twin_pivots(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().twin_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,240 @@
+// C ABI of libppgpu (include/ppgpu.h): handle management and the level-wise entry points.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ppgpu.h"
+#include "common.cuh"
+#include "host_math.hpp"
+#include "launch.h"
+
+using namespace ppgpu;
+
+static thread_local std::string g_err;
+
+struct ppgpu_program {
+    ReducedProgram host;
+    DevProgram dev;
+    int device = 0;
+    int sm_count = 0;
+    std::vector<void*> allocs;
+    unsigned long long* d_counters = nullptr;  // CNT_COUNT
+    unsigned long long* d_queue = nullptr;     // work-queue heads, one per launch in flight
+    int queue_slot = 0;
+    long long launches = 0;
+};
+
+static const int QUEUE_SLOTS = 64;
+
+static int fail(const char* where, cudaError_t e) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return -1;
+}
+static int fail_msg(const std::string& m) { g_err = m; return -2; }
+
+template <class T>
+static cudaError_t upload(ppgpu_program* p, const std::vector<T>& v, const T** out) {
+    void* d = nullptr;
+    const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return e;
+    p->allocs.push_back(d);
+    if (v.size()) e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T*)d;
+    return e;
+}
+
+static unsigned long long* next_queue(ppgpu_program* p, cudaStream_t st) {
+    unsigned long long* q = p->d_queue + p->queue_slot;
+    p->queue_slot = (p->queue_slot + 1) % QUEUE_SLOTS;
+    cudaMemsetAsync(q, 0, sizeof(unsigned long long), st);
+    return q;
+}
+
+extern "C" {
+
+const char* ppgpu_last_error(void) { return g_err.c_str(); }
+int ppgpu_version(void) { return 100; }
+
+int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, const double* F, const double* A_t,
+                         const double* b_t, const double* Q, const double* c, const double* H, int device,
+                         ppgpu_program** out) {
+    if (!d || !out) return fail_msg("null argument");
+    if (d->is_qp && !Q) return fail_msg("is_qp set but Q is NULL");
+    ppgpu_program* p = new ppgpu_program();
+    if (!reduce_program(d->n, d->t, d->m, d->q, d->n_eq, d->is_qp, A, b, F, A_t, b_t, Q, c, H, p->host)) {
+        std::string m = "program reduction failed: " + p->host.error;
+        delete p;
+        return fail_msg(m);
+    }
+    const ReducedProgram& R = p->host;
+    if (R.W > 4) { delete p; return fail_msg("more than 256 inequality rows are not supported"); }
+    if (R.R0 > 256) { delete p; return fail_msg("more than 256 region rows ((m - n_eq) + q) are not supported"); }
+    if (k2_pad_columns(R.nfree + 2) < 0) { delete p; return fail_msg("n - n_eq + t + 2 > 64 columns are not supported"); }
+    if (R.t + 2 > 16) { delete p; return fail_msg("more than 14 parameters are not supported"); }
+    if (R.np > 64) { delete p; return fail_msg("n - n_eq > 64 is not supported"); }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete p; return fail("cudaSetDevice", e); }
+    p->device = device;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    DevProgram& D = p->dev;
+    D.n = R.n; D.t = R.t; D.m = R.m; D.q = R.q; D.ne = R.ne; D.is_qp = R.is_qp;
+    D.mi = R.mi; D.np = R.np; D.W = R.W; D.R0 = R.R0; D.nfree = R.nfree; D.use_gram = R.use_gram;
+    D.dc0 = R.nfree + 2;
+#define UP(field, vecname) if ((e = upload(p, R.vecname, &D.field)) != cudaSuccess) { ppgpu_program_destroy(p); return fail("upload " #field, e); }
+    UP(At, At) UP(T0, T0) UP(G, G) UP(V, V) UP(A, A) UP(b, b) UP(F, F) UP(A_t, At_theta) UP(b_t, bt) UP(Q, Q) UP(c, c) UP(H, H)
+#undef UP
+    void* dc = nullptr;
+    if ((e = cudaMalloc(&dc, (CNT_COUNT + QUEUE_SLOTS) * sizeof(unsigned long long))) != cudaSuccess) {
+        ppgpu_program_destroy(p);
+        return fail("cudaMalloc counters", e);
+    }
+    p->allocs.push_back(dc);
+    cudaMemset(dc, 0, (CNT_COUNT + QUEUE_SLOTS) * sizeof(unsigned long long));
+    p->d_counters = (unsigned long long*)dc;
+    p->d_queue = p->d_counters + CNT_COUNT;
+    *out = p;
+    return 0;
+}
+
+int ppgpu_program_destroy(ppgpu_program* p) {
+    if (!p) return 0;
+    for (void* d : p->allocs) cudaFree(d);
+    delete p;
+    return 0;
+}
+
+int ppgpu_program_info(const ppgpu_program* p, ppgpu_info* o) {
+    if (!p || !o) return fail_msg("null argument");
+    const ReducedProgram& R = p->host;
+    o->words = R.W; o->n_ineq = R.mi; o->region_rows = R.R0; o->use_gram = R.use_gram;
+    o->max_depth = (R.n > R.t ? R.n : R.t) - R.ne;
+    o->sm_count = p->sm_count;
+    o->lp_columns = k2_pad_columns(R.nfree + 2);
+    o->reserved = 0;
+    return 0;
+}
+
+int ppgpu_root_level(ppgpu_program* p, uint64_t* d_masks, int64_t* h_count, ppgpu_stream stream) {
+    if (!p || !h_count) return fail_msg("null argument");
+    long long cnt = 0;
+    cudaError_t e = root_level(p->dev, d_masks, &cnt, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("root_level", e);
+    p->launches += cnt > 0;
+    *h_count = cnt;
+    return 0;
+}
+
+int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
+                     int32_t stages, ppgpu_stream stream) {
+    if (!p) return fail_msg("null argument");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (stages & 1) {
+        e = launch_k1(p->dev, d_masks, n, k_act, d_status, p->d_counters, p->sm_count, st);
+        if (e != cudaSuccess) return fail("K1 rank", e);
+        p->launches++;
+    }
+    if (stages & 2) {
+        e = launch_k2(p->dev, d_masks, n, d_status, next_queue(p, st), p->d_counters, p->sm_count, st);
+        if (e != cudaSuccess) return fail("K2 feasibility", e);
+        p->launches++;
+    }
+    if (stages & 4) {
+        if (p->dev.is_qp && p->dev.use_gram) {
+            e = launch_k34(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st);
+        } else {
+            e = launch_mark_general(p->dev, n, k_act, d_status, st);
+        }
+        if (e != cudaSuccess) return fail("K3/K4 optimality screen", e);
+        p->launches++;
+    }
+    return 0;
+}
+
+size_t ppgpu_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n); }
+
+int ppgpu_level_select(ppgpu_program* p, const uint8_t* d_status, int64_t n, uint8_t bits, uint8_t value,
+                       int64_t* d_idx_out, int64_t* h_count, void* d_ws, size_t ws_bytes, ppgpu_stream stream) {
+    if (!p || !h_count) return fail_msg("null argument");
+    *h_count = 0;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the count lands in the last workspace word, then comes back to the host
+    if (ws_bytes < scan_workspace_bytes(n)) return fail_msg("workspace too small");
+    long long* d_count = (long long*)d_ws + (scan_workspace_bytes(n) / sizeof(long long) - 1);
+    cudaError_t e = select_indices(d_status, n, bits, value, (long long*)d_idx_out, d_count, d_ws,
+                                   ws_bytes - sizeof(long long), st);
+    if (e != cudaSuccess) return fail("select", e);
+    p->launches += 5;
+    long long cnt = 0;
+    e = cudaMemcpyAsync(&cnt, d_count, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("select count", e);
+    *h_count = cnt;
+    return 0;
+}
+
+int ppgpu_regions_emit(ppgpu_program* p, const uint64_t* d_masks, const int64_t* d_sel, int64_t n_sel, int32_t k_act,
+                       double* d_laws, double* d_rows, int32_t* d_flags, double* d_info, uint8_t* d_status,
+                       ppgpu_stream stream) {
+    if (!p) return fail_msg("null argument");
+    if (n_sel <= 0) return 0;
+    cudaError_t e = launch_k5(p->dev, d_masks, (const long long*)d_sel, n_sel, k_act, d_laws, d_rows, d_flags, d_info,
+                              d_status, p->d_counters, p->sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("K5 emit", e);
+    p->launches++;
+    return 0;
+}
+
+int ppgpu_children_count(ppgpu_program* p, const uint64_t* d_masks, const int64_t* d_feas_idx, int64_t nf,
+                         int32_t k_act, uint64_t* d_feas_masks, uint64_t* d_survive, int64_t* d_offsets,
+                         int64_t* h_total, void* d_ws, size_t ws_bytes, ppgpu_stream stream) {
+    if (!p || !h_total) return fail_msg("null argument");
+    *h_total = 0;
+    if (nf <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = children_count(p->dev, d_masks, (const long long*)d_feas_idx, nf, k_act, d_feas_masks, d_survive,
+                                   (long long*)d_offsets, d_ws, ws_bytes, p->d_counters, st);
+    if (e != cudaSuccess) return fail("K6 count", e);
+    p->launches += 5;
+    long long tot = 0;
+    e = cudaMemcpyAsync(&tot, (long long*)d_offsets + nf, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("K6 total", e);
+    *h_total = tot;
+    return 0;
+}
+
+int ppgpu_children_write(ppgpu_program* p, const uint64_t* d_feas_masks, const uint64_t* d_survive,
+                         const int64_t* d_offsets, int64_t nf, uint64_t* d_children, ppgpu_stream stream) {
+    if (!p) return fail_msg("null argument");
+    cudaError_t e = children_write(p->dev, d_feas_masks, d_survive, (const long long*)d_offsets, nf, d_children,
+                                   (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("K6 write", e);
+    p->launches += nf > 0;
+    return 0;
+}
+
+int ppgpu_counters(ppgpu_program* p, uint64_t* h_out, int32_t reset, ppgpu_stream stream) {
+    if (!p || !h_out) return fail_msg("null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(h_out, p->d_counters, CNT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && reset) e = cudaMemsetAsync(p->d_counters, 0, CNT_COUNT * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return fail("counters", e);
+    return 0;
+}
+
+int64_t ppgpu_launch_count(const ppgpu_program* p) { return p ? p->launches : 0; }
+
+int ppgpu_measure_fp64_peak(int32_t iters, double* h_tflops, ppgpu_stream stream) {
+    if (!h_tflops) return fail_msg("null argument");
+    cudaError_t e = measure_fp64_peak(iters, h_tflops, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("fp64 peak", e);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// Shared device-side declarations of libppgpu (program constants as seen by the kernels, counters, bit helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tolerances.h"
+
+namespace ppgpu {
+
+// Program constants resident in HBM (a few tens of KB; L1/L2 resident in practice). Built once by
+// ppgpu_program_create from host_math.hpp::ReducedProgram. All matrices row-major fp64.
+struct DevProgram {
+    int n, t, m, q, ne, is_qp;
+    int mi, np, W, R0, nfree, use_gram;
+    int dc0;  // row stride of T0 = nfree + 2
+    const double* At;   // mi x np      reduced inequality rows (K1)
+    const double* T0;   // R0 x dc0     base feasibility tableau [rhs | v | theta | s] (K2)
+    const double* G;    // mi x mi      Gram  At Qr^-1 At'  (K3)
+    const double* V;    // mi x (t+1)   [const | theta] right-hand sides of the Schur system (K3)
+    const double* A; const double* b; const double* F;      // originals (K5)
+    const double* A_t; const double* b_t;
+    const double* Q; const double* c; const double* H;
+};
+
+// indices into the device counter array (uint64 each)
+enum Counter {
+    CNT_K1_CAND = 0,
+    CNT_K2_LPS, CNT_K2_PIVOTS, CNT_K2_WORK,
+    CNT_K4_LPS, CNT_K4_PIVOTS, CNT_K4_WORK,
+    CNT_K5_LPS, CNT_K5_PIVOTS, CNT_K5_WORK,
+    CNT_NUMERIC, CNT_BORDER, CNT_K6_LOOKUPS,
+    CNT_COUNT = 16
+};
+
+__device__ __forceinline__ bool mask_test(const uint64_t* m, int i) { return (m[i >> 6] >> (i & 63)) & 1ull; }
+
+__device__ __forceinline__ int mask_popc(const uint64_t* m, int W) {
+    int c = 0;
+    for (int w = 0; w < W; ++w) c += __popcll(m[w]);
+    return c;
+}
+
+// index of the j-th (0-based) set bit, -1 if there are fewer
+__device__ __forceinline__ int mask_nth(const uint64_t* m, int W, int j) {
+    for (int w = 0; w < W; ++w) {
+        const uint64_t x = m[w];
+        const int c = __popcll(x);
+        if (j < c) {
+            const unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+            const int cl = __popc(lo);
+            if (j < cl) return w * 64 + (int)__fns(lo, 0, j + 1);
+            return w * 64 + 32 + (int)__fns(hi, 0, j - cl + 1);
+        }
+        j -= c;
+    }
+    return -1;
+}
+
+// number of set bits strictly below position i
+__device__ __forceinline__ int mask_rank(const uint64_t* m, int i) {
+    int c = 0;
+    const int w = i >> 6;
+    for (int k = 0; k < w; ++k) c += __popcll(m[k]);
+    const int b = i & 63;
+    if (b) c += __popcll(m[w] & ((1ull << b) - 1ull));
+    return c;
+}
+
+// highest set bit, -1 for an empty mask
+__device__ __forceinline__ int mask_last(const uint64_t* m, int W) {
+    for (int w = W - 1; w >= 0; --w)
+        if (m[w]) return w * 64 + 63 - __clzll((long long)m[w]);
+    return -1;
+}
+
+// lexicographic order of the (sorted) index lists of two equal-cardinality masks: <0, 0, >0
+__device__ __forceinline__ int mask_lex_cmp(const uint64_t* a, const uint64_t* b, int W) {
+    for (int w = 0; w < W; ++w) {
+        const uint64_t d = a[w] ^ b[w];
+        if (d) {
+            const uint64_t low = d & (~d + 1ull);
+            return (a[w] & low) ? -1 : 1;
+        }
+    }
+    return 0;
+}
+
+}  // namespace ppgpu

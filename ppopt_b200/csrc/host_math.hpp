@@ -1,0 +1,242 @@
+// Host-side (once per program) reduction of an mpQP/mpLP to the inequality-only data the kernels read.
+//
+// Reference objects this replaces the per-candidate re-derivation of:
+//   * equality rows are always active (reference invariant equality_indices == range(n_eq),
+//     /root/reference/src/ppopt/mplp_program.py:112-118), so they are eliminated ONCE here instead of
+//     inside every is_full_rank / check_feasibility / optimal_control_law call;
+//   * the strictly-convex KKT system of mpqp_program.py:182-190 is rewritten through the Schur
+//     complement  S = A_act Q^-1 A_act'  so a candidate only gathers a k'xk' block of a precomputed Gram.
+// Pure C++ (no CUDA) so that the CPU checker in oracle/ can reuse exactly the same program reduction.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ppgpu {
+
+typedef std::vector<double> vec;
+
+struct ReducedProgram {
+    // dimensions
+    int n = 0, t = 0, m = 0, q = 0, ne = 0, is_qp = 0;
+    int mi = 0;        // inequality rows of the main constraint body (m - ne)
+    int np = 0;        // free x-directions after eliminating the equalities (n - ne)
+    int W = 1;         // 64-bit words per active-set bitmask
+    int R0 = 0;        // rows of the (x,theta) feasibility LP / of the theta-space region polytope: mi + q
+    int nfree = 0;     // np + t free variables of the feasibility LP
+    int use_gram = 0;  // 1: Q symmetric positive definite on the reduced space -> Gram/Cholesky screen
+    // K1: reduced inequality rows  At (mi x np)
+    vec At;
+    // K2: base tableau rows (R0 x (nfree + 2)), column layout [rhs | v(np) | theta(t) | s]
+    vec T0;
+    // K3: Gram G (mi x mi) and V (mi x (t+1)) with layout [const | theta coefficients]
+    vec G, V;
+    // originals (row major), kept for region emission
+    vec A, b, F, At_theta, bt, Q, c, H;
+    std::string error;
+};
+
+inline bool cholesky_lower(vec& M, int n) {  // in place, lower triangle; returns false if not PD
+    for (int j = 0; j < n; ++j) {
+        double d = M[j * n + j];
+        for (int k = 0; k < j; ++k) d -= M[j * n + k] * M[j * n + k];
+        if (!(d > 0.0) || !std::isfinite(d)) return false;
+        d = std::sqrt(d);
+        M[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = M[i * n + j];
+            for (int k = 0; k < j; ++k) s -= M[i * n + k] * M[j * n + k];
+            M[i * n + j] = s / d;
+        }
+    }
+    return true;
+}
+
+// Householder QR of an (r x c) matrix M (row major, r >= c); returns the full orthogonal factor Qf (r x r)
+// and leaves R in the upper triangle of M.
+inline void householder_qr_full(vec& M, int r, int c, vec& Qf) {
+    Qf.assign((size_t)r * r, 0.0);
+    for (int i = 0; i < r; ++i) Qf[(size_t)i * r + i] = 1.0;
+    vec v(r);
+    for (int j = 0; j < c; ++j) {
+        double nrm = 0.0;
+        for (int i = j; i < r; ++i) nrm += M[(size_t)i * c + j] * M[(size_t)i * c + j];
+        nrm = std::sqrt(nrm);
+        if (nrm == 0.0) continue;
+        double alpha = M[(size_t)j * c + j] >= 0 ? -nrm : nrm;
+        double vtv = 0.0;
+        for (int i = 0; i < r; ++i) v[i] = 0.0;
+        for (int i = j; i < r; ++i) v[i] = M[(size_t)i * c + j];
+        v[j] -= alpha;
+        for (int i = j; i < r; ++i) vtv += v[i] * v[i];
+        if (vtv == 0.0) continue;
+        for (int cc = j; cc < c; ++cc) {  // M <- (I - 2vv'/v'v) M
+            double d = 0.0;
+            for (int i = j; i < r; ++i) d += v[i] * M[(size_t)i * c + cc];
+            d = 2.0 * d / vtv;
+            for (int i = j; i < r; ++i) M[(size_t)i * c + cc] -= d * v[i];
+        }
+        for (int rr = 0; rr < r; ++rr) {  // Qf <- Qf (I - 2vv'/v'v)
+            double d = 0.0;
+            for (int i = j; i < r; ++i) d += Qf[(size_t)rr * r + i] * v[i];
+            d = 2.0 * d / vtv;
+            for (int i = j; i < r; ++i) Qf[(size_t)rr * r + i] -= d * v[i];
+        }
+    }
+}
+
+// Builds the reduced program. Inputs are row-major, equalities are rows 0..ne-1 of A/b/F.
+// Q may be null for an mpLP. Returns false (and sets out.error) on malformed input.
+inline bool reduce_program(int n, int t, int m, int q, int ne, int is_qp, const double* A, const double* b,
+                           const double* F, const double* A_t, const double* b_t, const double* Q, const double* c,
+                           const double* H, ReducedProgram& out) {
+    ReducedProgram& P = out;
+    P.n = n; P.t = t; P.m = m; P.q = q; P.ne = ne; P.is_qp = is_qp;
+    if (n < 0 || t < 1 || m < 0 || q < 0 || ne < 0 || ne > m || ne > n) { P.error = "bad dimensions"; return false; }
+    P.mi = m - ne; P.np = n - ne; P.R0 = P.mi + q; P.nfree = P.np + t;
+    P.W = P.mi <= 64 ? 1 : (P.mi + 63) / 64;
+    P.A.assign(A, A + (size_t)m * n); P.b.assign(b, b + m); P.F.assign(F, F + (size_t)m * t);
+    P.At_theta.assign(A_t, A_t + (size_t)q * t); P.bt.assign(b_t, b_t + q);
+    P.c.assign(c, c + n); P.H.assign(H, H + (size_t)n * t);
+    if (is_qp) P.Q.assign(Q, Q + (size_t)n * n); else P.Q.assign((size_t)n * n, 0.0);
+    const int np = P.np, mi = P.mi;
+    // ---- eliminate the equalities: x = x0 + Xt*theta + Q2*v
+    vec Q2((size_t)n * np, 0.0), x0(n, 0.0), Xt((size_t)n * t, 0.0);
+    if (ne == 0) {
+        for (int i = 0; i < n; ++i) Q2[(size_t)i * np + i] = 1.0;
+    } else {
+        vec M((size_t)n * ne), Qf;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < ne; ++j) M[(size_t)i * ne + j] = A[(size_t)j * n + i];
+        householder_qr_full(M, n, ne, Qf);
+        double rmax = 0.0;
+        for (int j = 0; j < ne; ++j) rmax = std::fmax(rmax, std::fabs(M[(size_t)j * ne + j]));
+        for (int j = 0; j < ne; ++j)
+            if (!(std::fabs(M[(size_t)j * ne + j]) > 1e-12 * rmax)) { P.error = "equality rows are rank deficient"; return false; }
+        // y1 = R^-T rhs, rhs columns = [b_eq | F_eq]; R' is lower triangular: (R')_{ij} = R_{ji}
+        vec Y((size_t)ne * (t + 1));
+        for (int col = 0; col <= t; ++col)
+            for (int i = 0; i < ne; ++i) {
+                double s = col == 0 ? b[i] : F[(size_t)i * t + col - 1];
+                for (int k = 0; k < i; ++k) s -= M[(size_t)k * ne + i] * Y[(size_t)k * (t + 1) + col];
+                Y[(size_t)i * (t + 1) + col] = s / M[(size_t)i * ne + i];
+            }
+        for (int i = 0; i < n; ++i) {
+            for (int col = 0; col <= t; ++col) {
+                double s = 0.0;
+                for (int k = 0; k < ne; ++k) s += Qf[(size_t)i * n + k] * Y[(size_t)k * (t + 1) + col];
+                if (col == 0) x0[i] = s; else Xt[(size_t)i * t + col - 1] = s;
+            }
+            for (int j = 0; j < np; ++j) Q2[(size_t)i * np + j] = Qf[(size_t)i * n + ne + j];
+        }
+    }
+    // ---- reduced inequality rows
+    P.At.assign((size_t)mi * np, 0.0);
+    vec Ft((size_t)mi * t, 0.0), bti(mi, 0.0);
+    for (int i = 0; i < mi; ++i) {
+        const double* Ai = A + (size_t)(ne + i) * n;
+        for (int j = 0; j < np; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += Ai[k] * Q2[(size_t)k * np + j];
+            P.At[(size_t)i * np + j] = s;
+        }
+        for (int j = 0; j < t; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += Ai[k] * Xt[(size_t)k * t + j];
+            Ft[(size_t)i * t + j] = F[(size_t)(ne + i) * t + j] - s;
+        }
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += Ai[k] * x0[k];
+        bti[i] = b[ne + i] - s;
+    }
+    // ---- K2 base tableau: row = [rhs | At_i | -Ft_i | 1]  and  [bt | 0 | A_t | 1]
+    const int dc = P.nfree + 2;
+    P.T0.assign((size_t)P.R0 * dc, 0.0);
+    for (int i = 0; i < mi; ++i) {
+        double* r = &P.T0[(size_t)i * dc];
+        r[0] = bti[i];
+        for (int j = 0; j < np; ++j) r[1 + j] = P.At[(size_t)i * np + j];
+        for (int j = 0; j < t; ++j) r[1 + np + j] = -Ft[(size_t)i * t + j];
+        r[1 + np + t] = 1.0;
+    }
+    for (int i = 0; i < q; ++i) {
+        double* r = &P.T0[(size_t)(mi + i) * dc];
+        r[0] = b_t[i];
+        for (int j = 0; j < t; ++j) r[1 + np + j] = A_t[(size_t)i * t + j];
+        r[1 + np + t] = 1.0;
+    }
+    // ---- K3 Gram data (only when the reduced Hessian is symmetric positive definite)
+    P.use_gram = 0;
+    P.G.assign((size_t)mi * mi, 0.0);
+    P.V.assign((size_t)mi * (t + 1), 0.0);
+    if (is_qp) {
+        double asym = 0.0, qmax = 0.0;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+            asym = std::fmax(asym, std::fabs(Q[(size_t)i * n + j] - Q[(size_t)j * n + i]));
+            qmax = std::fmax(qmax, std::fabs(Q[(size_t)i * n + j]));
+        }
+        bool sym = asym <= 1e-12 * qmax;
+        // Qr = Q2' Q Q2, rhs_lin = Q2'(Q [x0 | Xt] + [c | H])
+        vec QQ2((size_t)n * np, 0.0), Qr((size_t)np * np, 0.0), lin((size_t)np * (t + 1), 0.0);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < np; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += Q[(size_t)i * n + k] * Q2[(size_t)k * np + j];
+            QQ2[(size_t)i * np + j] = s;
+        }
+        for (int i = 0; i < np; ++i) for (int j = 0; j < np; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += Q2[(size_t)k * np + i] * QQ2[(size_t)k * np + j];
+            Qr[(size_t)i * np + j] = s;
+        }
+        for (int col = 0; col <= t; ++col) {
+            vec w(n);
+            for (int i = 0; i < n; ++i) {
+                double s = col == 0 ? c[i] : H[(size_t)i * t + col - 1];
+                for (int k = 0; k < n; ++k) s += Q[(size_t)i * n + k] * (col == 0 ? x0[k] : Xt[(size_t)k * t + col - 1]);
+                w[i] = s;
+            }
+            for (int j = 0; j < np; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s += Q2[(size_t)k * np + j] * w[k];
+                lin[(size_t)j * (t + 1) + col] = s;
+            }
+        }
+        for (int i = 0; i < np; ++i) for (int j = 0; j < i; ++j) {
+            double a = 0.5 * (Qr[(size_t)i * np + j] + Qr[(size_t)j * np + i]);
+            Qr[(size_t)i * np + j] = Qr[(size_t)j * np + i] = a;
+        }
+        vec L = Qr;
+        if (sym && cholesky_lower(L, np)) {
+            // Y = L^-1 At' (np x mi), Z = L^-1 lin (np x (t+1))
+            vec Y((size_t)np * mi), Z((size_t)np * (t + 1));
+            for (int col = 0; col < mi; ++col)
+                for (int i = 0; i < np; ++i) {
+                    double s = P.At[(size_t)col * np + i];
+                    for (int k = 0; k < i; ++k) s -= L[(size_t)i * np + k] * Y[(size_t)k * mi + col];
+                    Y[(size_t)i * mi + col] = s / L[(size_t)i * np + i];
+                }
+            for (int col = 0; col <= t; ++col)
+                for (int i = 0; i < np; ++i) {
+                    double s = lin[(size_t)i * (t + 1) + col];
+                    for (int k = 0; k < i; ++k) s -= L[(size_t)i * np + k] * Z[(size_t)k * (t + 1) + col];
+                    Z[(size_t)i * (t + 1) + col] = s / L[(size_t)i * np + i];
+                }
+            for (int i = 0; i < mi; ++i) {
+                for (int j = 0; j <= i; ++j) {
+                    double s = 0.0;
+                    for (int k = 0; k < np; ++k) s += Y[(size_t)k * mi + i] * Y[(size_t)k * mi + j];
+                    P.G[(size_t)i * mi + j] = P.G[(size_t)j * mi + i] = s;
+                }
+                for (int col = 0; col <= t; ++col) {
+                    double s = col == 0 ? bti[i] : Ft[(size_t)i * t + col - 1];
+                    for (int k = 0; k < np; ++k) s += Y[(size_t)k * mi + i] * Z[(size_t)k * (t + 1) + col];
+                    P.V[(size_t)i * (t + 1) + col] = s;
+                }
+            }
+            P.use_gram = 1;
+        }
+    }
+    return true;
+}
+
+}  // namespace ppgpu

@@ -1,0 +1,129 @@
+// K1 - LICQ rank screen, one warp per candidate, one lane per active row.
+//
+// Replaces is_full_rank(A, active_set) = (numpy.linalg.matrix_rank(A[active_set]) == |active_set|)
+// (/root/reference/src/ppopt/utils/constraint_utilities.py:222-236, called from mplp_program.py:433-435).
+// The program's equality rows are already projected out (host_math.hpp), so rank(A_active) = n_eq + rank of the
+// k' reduced rows.  Column-pivoted Householder QR of the np x k' matrix: lane j keeps column j (= reduced row of the
+// j-th active constraint) in registers, the pivot column is broadcast with shuffles, every lane reflects its own
+// column.  Deficient iff |R_ss| <= PPG_RANK_TOL * |R_00|; ratios inside [PPG_RANK_BORDER_LO, PPG_RANK_BORDER_HI]
+// raise PPG_ST_BORDER so that a borderline decision is never silent.
+#include "common.cuh"
+#include "launch.h"
+#include "lp_core.cuh"
+
+namespace ppgpu {
+
+template <int NP, int KPL>
+__global__ void __launch_bounds__(128)
+k1_rank_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
+               unsigned long long* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int W = P.W, np = P.np;
+    unsigned long long n_border = 0;
+    for (long long idx = warp0; idx < n; idx += nwarps) {
+        const uint64_t* mk = masks + idx * W;
+        uint8_t st = 0;
+        const int k = k_act >= 0 ? k_act : mask_popc(mk, W);
+        if (k == 0) {
+            st = PPG_ST_RANK;
+        } else if (k > np || k > 32 * KPL) {
+            st = 0;
+        } else {
+            double col[KPL][NP];
+            bool done[KPL];
+#pragma unroll
+            for (int kk = 0; kk < KPL; ++kk) {
+                const int j = kk * 32 + lane;
+                done[kk] = j >= k;
+                const int a = (j < k) ? mask_nth(mk, W, j) : -1;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) col[kk][i] = (a >= 0 && i < np) ? __ldg(P.At + (size_t)a * np + i) : 0.0;
+            }
+            double first = 0.0, minratio = 1.0;
+            bool full = true;
+            for (int s = 0; s < k; ++s) {
+                // pivot = remaining column of largest trailing norm
+                double best = -1.0; int pj = 0x7fffffff;
+#pragma unroll
+                for (int kk = 0; kk < KPL; ++kk) {
+                    if (!done[kk]) {
+                        double nn = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) if (i >= s) nn = fma(col[kk][i], col[kk][i], nn);
+                        if (nn > best) { best = nn; pj = kk * 32 + lane; }
+                    }
+                }
+                warp_argmax(best, pj);
+                const double rss = sqrt(best);
+                if (s == 0) first = rss;
+                if (first == 0.0) { full = false; minratio = 0.0; break; }
+                const double ratio = rss / first;
+                minratio = fmin(minratio, ratio);
+                if (ratio <= PPG_RANK_TOL) { full = false; break; }
+                // broadcast the pivot column, build the Householder vector v (rows s..np-1)
+                double v[NP];
+                const int src = pj & 31, slot = pj >> 5;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < KPL; ++kk) if (kk == slot) x = col[kk][i];
+                    v[i] = (i >= s) ? shfl_d(x, src) : 0.0;
+                }
+                double vs = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) if (i == s) vs = v[i];
+                const double alpha = vs >= 0.0 ? -rss : rss;
+                double vtv = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    if (i == s) v[i] -= alpha;
+                    vtv = fma(v[i], v[i], vtv);
+                }
+#pragma unroll
+                for (int kk = 0; kk < KPL; ++kk) {
+                    if (kk * 32 + lane == pj) done[kk] = true;
+                    if (!done[kk] && vtv > 0.0) {
+                        double d = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) d = fma(v[i], col[kk][i], d);
+                        d = 2.0 * d / vtv;
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) col[kk][i] = fma(-d, v[i], col[kk][i]);
+                    }
+                }
+            }
+            if (full) st = PPG_ST_RANK;
+            if (minratio > PPG_RANK_BORDER_LO && minratio < PPG_RANK_BORDER_HI) { st |= PPG_ST_BORDER; n_border++; }
+        }
+        if (lane == 0) status[idx] = st;
+    }
+    if (lane == 0) {
+        if (n_border) atomicAdd(&counters[CNT_BORDER], n_border);
+    }
+}
+
+template <int NP, int KPL>
+static cudaError_t launch_k1_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                               unsigned long long* counters, int sm_count, cudaStream_t st) {
+    const int threads = 128;
+    long long blocks = (n * 32 + threads - 1) / threads;
+    const long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k1_rank_kernel<NP, KPL><<<(unsigned)blocks, threads, 0, st>>>(P, masks, n, k_act, status, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                      unsigned long long* counters, int sm_count, cudaStream_t st) {
+    if (P.np <= 8) return launch_k1_t<8, 1>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (P.np <= 16) return launch_k1_t<16, 1>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (P.np <= 32) return launch_k1_t<32, 1>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (P.np <= 64) return launch_k1_t<64, 2>(P, masks, n, k_act, status, counters, sm_count, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace ppgpu

@@ -1,0 +1,151 @@
+// K2 - batched feasibility LP, one LP per group of NW warps, tableau in registers.
+//
+// Replaces, per candidate active set, MPLP_Program.check_feasibility's LP
+//   exists (x,theta):  A x - F theta <= b,  A_t theta <= b_t,  rows of the active set as equalities
+// (/root/reference/src/ppopt/mplp_program.py:439-444 -> solver.py:211-246 -> cvxopt_interface.py:153-208),
+// the call the serial reference spends 45-50 % of its time in.
+// The program's own equalities are already eliminated (host_math.hpp), so the tableau has R0 = mi + q rows and
+// nfree + 2 columns [rhs | v | theta | s]; the candidate's active inequality rows are pivoted out first, then
+// s = min slack is maximised and the solve stops as soon as s >= -PPG_FEAS_TOL.
+#include "common.cuh"
+#include "lp_core.cuh"
+#include "launch.h"
+
+namespace ppgpu {
+
+template <int NW, int RPT, int DC, int WPC>
+__global__ void __launch_bounds__(NW * 32 * WPC)
+k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, uint8_t* __restrict__ status,
+               unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters) {
+    typedef LpCore<NW, RPT, DC> Core;
+    constexpr int GT = NW * 32;
+    __shared__ typename Core::Shared sh_all[WPC];
+    __shared__ long long next_item[WPC];
+    const int grp = (NW == 1) ? (threadIdx.x >> 5) : 0;
+    const int tid = (NW == 1) ? (threadIdx.x & 31) : threadIdx.x;
+    typename Core::Shared& sh = sh_all[grp];
+    unsigned long long n_lp = 0, n_piv = 0, n_work = 0, n_num = 0;
+    const int W = P.W;
+    for (;;) {
+        long long idx;
+        if constexpr (NW == 1) {
+            unsigned long long v = 0;
+            if (tid == 0) v = atomicAdd(queue, 1ull);
+            idx = (long long)__shfl_sync(PPG_FULL, v, 0);
+        } else {
+            if (tid == 0) next_item[0] = (long long)atomicAdd(queue, 1ull);
+            __syncthreads();
+            idx = next_item[0];
+            __syncthreads();
+        }
+        if (idx >= n) break;
+        const uint8_t st = status[idx];
+        if (!(st & PPG_ST_RANK)) continue;
+        const uint64_t* mk = masks + idx * W;
+        double T[RPT][DC];
+        int rflag[RPT];
+        const int js = P.nfree + 1;
+        static_for<RPT>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            const int row = rr * GT + tid;
+            if (row < P.R0) {
+                const double* src = P.T0 + (size_t)row * P.dc0;
+#pragma unroll
+                for (int c = 0; c < DC; ++c) T[rr][c] = (c < P.dc0) ? __ldg(src + c) : 0.0;
+                rflag[rr] = 1;
+                if (row < P.mi && mask_test(mk, row)) {
+                    rflag[rr] = 2;
+                    reg_zero<DC>(T[rr], js);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < DC; ++c) T[rr][c] = 0.0;
+                rflag[rr] = 0;
+            }
+        });
+        LpOut res = Core::solve(sh, T, rflag, P.R0, js, -PPG_FEAS_TOL, false, tid);
+        const bool feas = res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED ||
+                          (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_FEAS_TOL);
+        if (tid == 0) {
+            uint8_t s2 = st;
+            if (feas) s2 |= PPG_ST_FEAS;
+            if (res.code == PPG_LP_ITERLIM) { s2 |= PPG_ST_NUMERIC; n_num++; }
+            status[idx] = s2;
+            n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
+        }
+        if constexpr (NW > 1) __syncthreads();
+    }
+    if (tid == 0 && n_lp) {
+        atomicAdd(&counters[CNT_K2_LPS], n_lp);
+        atomicAdd(&counters[CNT_K2_PIVOTS], n_piv);
+        atomicAdd(&counters[CNT_K2_WORK], n_work);
+        if (n_num) atomicAdd(&counters[CNT_NUMERIC], n_num);
+    }
+}
+
+template <int NW, int RPT, int DC>
+static cudaError_t launch_k2_t(const DevProgram& P, const uint64_t* masks, long long n, uint8_t* status,
+                               unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st) {
+    constexpr int WPC = (NW == 1) ? 4 : 1;
+    auto kern = k2_feas_kernel<NW, RPT, DC, WPC>;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32 * WPC, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    long long groups_needed = (n + WPC - 1) / WPC;
+    long long grid = (long long)sm_count * occ;
+    if (grid > groups_needed) grid = groups_needed;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, NW * 32 * WPC, 0, st>>>(P, masks, n, status, queue, counters);
+    return cudaGetLastError();
+}
+
+#define K2_DC_SWITCH(NW, RPT)                                                                          \
+    switch (dc) {                                                                                      \
+        case 8: return launch_k2_t<NW, RPT, 8>(P, masks, n, status, queue, counters, sm_count, st);    \
+        case 16: return launch_k2_t<NW, RPT, 16>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 24: return launch_k2_t<NW, RPT, 24>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 32: return launch_k2_t<NW, RPT, 32>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 40: return launch_k2_t<NW, RPT, 40>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 48: return launch_k2_t<NW, RPT, 48>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 64: return launch_k2_t<NW, RPT, 64>(P, masks, n, status, queue, counters, sm_count, st);  \
+        default: return cudaErrorInvalidValue;                                                         \
+    }
+
+#define K2_DC_SWITCH_SMALL(NW, RPT)                                                                    \
+    switch (dc) {                                                                                      \
+        case 8: return launch_k2_t<NW, RPT, 8>(P, masks, n, status, queue, counters, sm_count, st);    \
+        case 16: return launch_k2_t<NW, RPT, 16>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 24: return launch_k2_t<NW, RPT, 24>(P, masks, n, status, queue, counters, sm_count, st);  \
+        default: return cudaErrorInvalidValue;                                                         \
+    }
+#define K2_DC_SWITCH_LARGE(NW, RPT)                                                                    \
+    switch (dc) {                                                                                      \
+        case 32: return launch_k2_t<NW, RPT, 32>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 40: return launch_k2_t<NW, RPT, 40>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 48: return launch_k2_t<NW, RPT, 48>(P, masks, n, status, queue, counters, sm_count, st);  \
+        case 64: return launch_k2_t<NW, RPT, 64>(P, masks, n, status, queue, counters, sm_count, st);  \
+        default: return cudaErrorInvalidValue;                                                         \
+    }
+
+int k2_pad_columns(int ncols_with_rhs) {
+    const int opts[] = {8, 16, 24, 32, 40, 48, 64};
+    for (int o : opts) if (ncols_with_rhs <= o) return o;
+    return -1;
+}
+
+// chooses the thread mapping from the tableau shape: rows -> warps, columns -> registers per thread
+cudaError_t launch_k2(const DevProgram& P, const uint64_t* masks, long long n, uint8_t* status,
+                      unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st) {
+    const int dc = k2_pad_columns(P.dc0);
+    if (dc < 0 || P.R0 > 256) return cudaErrorInvalidValue;
+    if (P.R0 <= 32) { K2_DC_SWITCH(1, 1) }
+    if (P.R0 <= 64) {
+        if (dc <= 24) { K2_DC_SWITCH_SMALL(1, 2) }
+        K2_DC_SWITCH_LARGE(2, 1)
+    }
+    if (P.R0 <= 128) { K2_DC_SWITCH(4, 1) }
+    K2_DC_SWITCH(8, 1)
+}
+
+}  // namespace ppgpu

@@ -1,0 +1,250 @@
+// K3 + K4 - KKT solve by Schur complement / Cholesky and the theta-space optimality + full-dimension test.
+// One warp per feasible candidate.
+//
+// Reference work replaced, per candidate:
+//   check_optimality       /root/reference/src/ppopt/mpqp_program.py:203-322   (an (n+t+m+1)-variable LP "max t")
+//   optimal_control_law    /root/reference/src/ppopt/mpqp_program.py:146-198   (two LU solves of the KKT matrix)
+//   region rows + filters  /root/reference/src/ppopt/utils/mpqp_utils.py:111-126
+//   is_full_dimensional    /root/reference/src/ppopt/utils/mpqp_utils.py:323-344 -> chebyshev_ball.py:10-63
+// For a nonsingular KKT system x(theta), lambda(theta) are unique affine maps, so the big optimality LP is feasible
+// iff the polytope { lambda_act(theta) >= 0, inactive slacks(theta) >= 0, A_t theta <= b_t } is non-empty
+// (the same reduction the reference itself uses in mp_solvers/mpqp_combi_graph.py:48-66); its Chebyshev radius then
+// decides full dimensionality.  With G = At Qr^-1 At' and V precomputed (host_math.hpp):
+//   S = G[act,act] (gather, k'xk')   Lambda = -S^-1 V[act]        (Cholesky + 2 triangular solves, t+1 rhs)
+//   lambda rows:   -Lambda_theta[j] . theta <= Lambda_const[j]
+//   inactive rows: -(V_theta[i] + G[i,act] Lambda_theta) . theta <= V_const[i] + G[i,act] Lambda_const
+// Zero rows (all |a| <= 1e-8) are dropped unless their rhs < -1e-7 (then the candidate is not optimal), rows are
+// L2-normalised and  max r : a.theta + r <= f  is solved by the register simplex of lp_core.cuh.
+// This kernel is a SCREEN (radius >= PPG_RADIUS_SCREEN); K5 repeats the test on LU-accurate rows before emitting.
+#include "common.cuh"
+#include "launch.h"
+#include "lp_core.cuh"
+
+namespace ppgpu {
+
+template <int RPT, int DC, int WPC>
+__global__ void __launch_bounds__(32 * WPC)
+k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
+           unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters) {
+    typedef LpCore<1, RPT, DC> Core;
+    extern __shared__ double dyn_smem[];
+    __shared__ typename Core::Shared sh_all[WPC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    typename Core::Shared& sh = sh_all[warp];
+    const int t = P.t, t1 = P.t + 1, mi = P.mi, W = P.W, kmax = k_act;
+    // per-warp scratch: S (kmax x kmax), Lam (kmax x t1), act (kmax ints)
+    const size_t per_warp = (size_t)kmax * kmax + (size_t)kmax * t1 + (size_t)((kmax + 1) / 2 + 1);
+    double* S = dyn_smem + per_warp * warp;
+    double* Lam = S + (size_t)kmax * kmax;
+    int* act = reinterpret_cast<int*>(Lam + (size_t)kmax * t1);
+    unsigned long long n_lp = 0, n_piv = 0, n_work = 0, n_num = 0;
+    for (;;) {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(queue, 1ull);
+        const long long idx = (long long)__shfl_sync(PPG_FULL, v, 0);
+        if (idx >= n) break;
+        const uint8_t st = status[idx];
+        if (!(st & PPG_ST_FEAS)) continue;
+        const uint64_t* mk = masks + idx * W;
+        const int k = kmax;
+        __syncwarp();
+        for (int j = lane; j < k; j += 32) act[j] = mask_nth(mk, W, j);
+        __syncwarp();
+        for (int e = lane; e < k * k; e += 32) {
+            const int a = e / k, b2 = e - a * k;
+            S[e] = __ldg(P.G + (size_t)act[a] * mi + act[b2]);
+        }
+        __syncwarp();
+        // Cholesky (lower), right-looking, lanes over rows
+        bool pd = true;
+        for (int j = 0; j < k; ++j) {
+            const double d = S[j * k + j];
+            if (!(d > 0.0)) { pd = false; break; }
+            const double sd = sqrt(d);
+            __syncwarp();
+            for (int i = j + 1 + lane; i < k; i += 32) S[i * k + j] /= sd;
+            if (lane == 0) S[j * k + j] = sd;
+            __syncwarp();
+            for (int i = j + 1 + lane; i < k; i += 32) {
+                const double lij = S[i * k + j];
+                for (int c = j + 1; c <= i; ++c) S[i * k + c] = fma(-lij, S[c * k + j], S[i * k + c]);
+            }
+            __syncwarp();
+        }
+        bool pass = false;
+        bool numeric = false;
+        if (!pd) {
+            numeric = true;
+        } else {
+            // Lambda = -S^-1 V[act]; lane c handles rhs column c (0 = constant term)
+            if (lane < t1) {
+                for (int i = 0; i < k; ++i) {
+                    double s = -__ldg(P.V + (size_t)act[i] * t1 + lane);
+                    for (int j = 0; j < i; ++j) s = fma(-S[i * k + j], Lam[j * t1 + lane], s);
+                    Lam[i * t1 + lane] = s / S[i * k + i];
+                }
+                for (int i = k - 1; i >= 0; --i) {
+                    double s = Lam[i * t1 + lane];
+                    for (int j = i + 1; j < k; ++j) s = fma(-S[j * k + i], Lam[j * t1 + lane], s);
+                    Lam[i * t1 + lane] = s / S[i * k + i];
+                }
+            }
+            __syncwarp();
+            // region rows straight into the tableau registers: T[.][0] = f, T[.][1..t] = a, T[.][t+1] = 1 (the s column)
+            double T[RPT][DC];
+            int rflag[RPT];
+            bool zero_viol = false;
+            static_for<RPT>([&](auto RR) {
+                constexpr int rr = decltype(RR)::value;
+                const int row = rr * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < DC; ++c) T[rr][c] = 0.0;
+                rflag[rr] = 0;
+                if (row < P.R0) {
+                    if (row < mi) {
+                        if (mask_test(mk, row)) {
+                            const int pos = mask_rank(mk, row);
+#pragma unroll
+                            for (int c = 0; c < DC; ++c)
+                                if (c < t1) T[rr][c] = (c == 0) ? Lam[pos * t1] : -Lam[pos * t1 + c];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < DC; ++c)
+                                if (c < t1) T[rr][c] = __ldg(P.V + (size_t)row * t1 + c);
+                            for (int a = 0; a < k; ++a) {
+                                const double g = __ldg(P.G + (size_t)row * mi + act[a]);
+#pragma unroll
+                                for (int c = 0; c < DC; ++c)
+                                    if (c < t1) T[rr][c] = fma(g, Lam[a * t1 + c], T[rr][c]);
+                            }
+#pragma unroll
+                            for (int c = 1; c < DC; ++c)
+                                if (c < t1) T[rr][c] = -T[rr][c];
+                        }
+                    } else {
+                        const int o = row - mi;
+                        T[rr][0] = __ldg(P.b_t + o);
+#pragma unroll
+                        for (int c = 1; c < DC; ++c)
+                            if (c < t1) T[rr][c] = __ldg(P.A_t + (size_t)o * t + c - 1);
+                    }
+                    double mx = 0.0, nn = 0.0;
+#pragma unroll
+                    for (int c = 1; c < DC; ++c)
+                        if (c < t1) { mx = fmax(mx, fabs(T[rr][c])); nn = fma(T[rr][c], T[rr][c], nn); }
+                    if (!(mx <= PPG_ZERO_ROW)) {
+                        const double inv = 1.0 / sqrt(nn);
+#pragma unroll
+                        for (int c = 0; c < DC; ++c)
+                            if (c < t1) T[rr][c] *= inv;
+                        rflag[rr] = 1;
+                    } else if (T[rr][0] < -PPG_FEAS_TOL) {
+                        zero_viol = true;
+                    }
+                }
+            });
+            const bool any_viol = __any_sync(PPG_FULL, zero_viol);
+            if (!any_viol) {
+                if (t == 1) {
+                    // interval [lo, hi] of the 1-D polytope (get_bounds_1d, mpqp_utils.py:304-315)
+                    double lo = -CUDART_INF, hi = CUDART_INF;
+                    static_for<RPT>([&](auto RR) {
+                        constexpr int rr = decltype(RR)::value;
+                        if (rflag[rr] == 1) {
+                            const double q = T[rr][0] / T[rr][1];
+                            if (T[rr][1] > 0.0) hi = fmin(hi, q); else lo = fmax(lo, q);
+                        }
+                    });
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo = fmax(lo, shfl_xor_d(lo, o));
+                        hi = fmin(hi, shfl_xor_d(hi, o));
+                    }
+                    pass = (lo + 0.5 * PPG_WIDTH_1D <= hi);
+                } else {
+                    static_for<RPT>([&](auto RR) {
+                        constexpr int rr = decltype(RR)::value;
+                        if (rflag[rr] == 1) {
+#pragma unroll
+                            for (int c = 0; c < DC; ++c)
+                                if (c == t1) T[rr][c] = 1.0;
+                        }
+                    });
+                    LpOut res = Core::solve(sh, T, rflag, P.R0, t1, PPG_RADIUS_SCREEN, false, lane);
+                    pass = res.code == PPG_LP_EARLY || (res.code == PPG_LP_OPTIMAL && res.beta >= PPG_RADIUS_SCREEN);
+                    if (res.code == PPG_LP_ITERLIM) numeric = true;
+                    n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
+                }
+            }
+        }
+        if (lane == 0) {
+            uint8_t s2 = st;
+            if (pass) s2 |= PPG_ST_OPT;
+            if (numeric) { s2 |= PPG_ST_NUMERIC; n_num++; }
+            if (s2 != st) status[idx] = s2;
+        }
+    }
+    if (lane == 0 && (n_lp || n_num)) {
+        atomicAdd(&counters[CNT_K4_LPS], n_lp);
+        atomicAdd(&counters[CNT_K4_PIVOTS], n_piv);
+        atomicAdd(&counters[CNT_K4_WORK], n_work);
+        if (n_num) atomicAdd(&counters[CNT_NUMERIC], n_num);
+    }
+}
+
+template <int RPT, int DC>
+static cudaError_t launch_k34_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                                unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st) {
+    constexpr int WPC = 4;
+    auto kern = k34_kernel<RPT, DC, WPC>;
+    const size_t per_warp = (size_t)k_act * k_act + (size_t)k_act * (P.t + 1) + (size_t)((k_act + 1) / 2 + 1);
+    const size_t smem = per_warp * WPC * sizeof(double);
+    cudaError_t e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPC, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sm_count * occ;
+    const long long need = (n + WPC - 1) / WPC;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 32 * WPC, smem, st>>>(P, masks, n, k_act, status, queue, counters);
+    return cudaGetLastError();
+}
+
+#define K34_RPT_SWITCH(DCV)                                                                                  \
+    if (P.R0 <= 32) return launch_k34_t<1, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st);  \
+    if (P.R0 <= 64) return launch_k34_t<2, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st);  \
+    if (P.R0 <= 128) return launch_k34_t<4, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st); \
+    if (P.R0 <= 256) return launch_k34_t<8, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st); \
+    return cudaErrorInvalidValue;
+
+cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st) {
+    if (P.t + 2 <= 8) { K34_RPT_SWITCH(8) }
+    if (P.t + 2 <= 16) { K34_RPT_SWITCH(16) }
+    return cudaErrorInvalidValue;
+}
+
+// general (non-Gram) path: every feasible candidate the reference would pass to check_optimality is handed to K5.
+// mpLP: only |active set| == n can be optimal (mplp_program.py:472-473).
+__global__ void mark_general_kernel(long long n, int pass_all, uint8_t* __restrict__ status) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint8_t st = status[i];
+        if ((st & PPG_ST_FEAS) && pass_all) status[i] = st | PPG_ST_OPT;
+    }
+}
+
+cudaError_t launch_mark_general(const DevProgram& P, long long n, int k_act, uint8_t* status, cudaStream_t st) {
+    const int pass_all = P.is_qp ? 1 : ((P.ne + k_act == P.n) ? 1 : 0);
+    if (n <= 0) return cudaSuccess;
+    mark_general_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, pass_all, status);
+    return cudaGetLastError();
+}
+
+}  // namespace ppgpu

@@ -1,0 +1,37 @@
+// Host-side launch entry points of the individual kernels (internal to libppgpu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace ppgpu {
+
+int k2_pad_columns(int ncols_with_rhs);
+
+cudaError_t launch_k1(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                      unsigned long long* counters, int sm_count, cudaStream_t st);
+cudaError_t launch_k2(const DevProgram& P, const uint64_t* masks, long long n, uint8_t* status,
+                      unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st);
+cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st);
+// general (LU) path: marks every feasible candidate that the reference would hand to check_optimality
+cudaError_t launch_mark_general(const DevProgram& P, long long n, int k_act, uint8_t* status, cudaStream_t st);
+
+cudaError_t launch_k5(const DevProgram& P, const uint64_t* masks, const long long* idx, long long n_sel, int k_act,
+                      double* laws, double* rows, int32_t* flags, double* info, uint8_t* status,
+                      unsigned long long* counters, int sm_count, cudaStream_t st);
+
+size_t scan_workspace_bytes(long long n);
+cudaError_t select_indices(const uint8_t* status, long long n, uint8_t bits, uint8_t value, long long* idx_out,
+                           long long* d_count, void* ws, size_t ws_bytes, cudaStream_t st);
+cudaError_t root_level(const DevProgram& P, uint64_t* masks, long long* d_count, cudaStream_t st);
+cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const long long* feas_idx, long long nf,
+                           int k_act, uint64_t* feas_masks, uint64_t* survive, long long* offsets, void* ws,
+                           size_t ws_bytes, unsigned long long* counters, cudaStream_t st);
+cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, const uint64_t* survive,
+                           const long long* offsets, long long nf, uint64_t* children, cudaStream_t st);
+
+cudaError_t measure_fp64_peak(int iters, double* tflops, cudaStream_t st);
+
+}  // namespace ppgpu

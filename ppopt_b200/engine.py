@@ -1,0 +1,355 @@
+"""Level-synchronous GPU driver behind mpqp_combinatorial.solve.
+
+Host mirror of the reference's level loop (/root/reference/src/ppopt/mp_solvers/mpqp_combinatorial.py:10-72):
+every enumeration level is ONE batch of candidate bitmasks that stays in HBM; the host only learns counts
+(feasible, optimal, children) and receives the matrices of the regions that were actually emitted.
+torch is used for device buffers, streams and torch.distributed - all arithmetic is in libppgpu.so.
+"""
+import ctypes
+import time
+from typing import Dict, List, Optional
+
+import numpy
+import torch
+
+from . import _lib
+from ._lib import ST_FEAS, ST_OPT, ST_REGION
+
+
+def _c(a):
+    return numpy.ascontiguousarray(numpy.asarray(a, dtype=numpy.float64))
+
+
+def program_arrays(program) -> Dict:
+    """Reads the attributes the reference's solver reads (mplp_program.py:45-58) from a ppopt or ppopt_b200 program."""
+    A = _c(program.A)
+    n = A.shape[1]
+    F = _c(program.F)
+    t = F.shape[1]
+    is_qp = hasattr(program, 'Q') and program.Q is not None and type(program).__name__ != 'MPLP_Program'
+    H = _c(program.H)
+    if H.shape != (n, t):
+        # some reference fixtures pass an all-zero H with the transposed shape (tests/test_fixtures.py:60,104)
+        if H.shape == (t, n) and not numpy.any(H):
+            H = numpy.zeros((n, t))
+        else:
+            raise ValueError(f'H must be num_x x num_t = {(n, t)}, got {H.shape}')
+    eq = [int(i) for i in program.equality_indices]
+    if eq != list(range(len(eq))):
+        raise ValueError('equality_indices must be range(n_eq) (the reference constructor guarantees it)')
+    out = dict(A=A, b=_c(program.b).reshape(-1), F=F, A_t=_c(program.A_t).reshape(-1, t),
+               b_t=_c(program.b_t).reshape(-1), c=_c(program.c).reshape(-1), H=H, n_eq=len(eq), is_qp=bool(is_qp))
+    out['Q'] = _c(program.Q) if is_qp else None
+    return out
+
+
+class Engine:
+    """Owns one ppgpu_program handle on one device."""
+
+    def __init__(self, arrays: Dict, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('ppopt_b200 needs a CUDA device (there is no CPU fallback)')
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tdev = torch.device('cuda', self.device)
+        a = arrays
+        self.n, self.t = a['A'].shape[1], a['F'].shape[1]
+        self.m, self.q, self.n_eq, self.is_qp = a['A'].shape[0], a['A_t'].shape[0], a['n_eq'], a['is_qp']
+        dims = _lib.Dims(self.n, self.t, self.m, self.q, self.n_eq, int(self.is_qp))
+        self._keep = a  # host arrays must outlive the create call only, kept for debugging
+        h = ctypes.c_void_p()
+        ptr = lambda x: None if x is None else x.ctypes.data
+        with torch.cuda.device(self.device):
+            rc = self.lib.ppgpu_program_create(ctypes.byref(dims), ptr(a['A']), ptr(a['b']), ptr(a['F']), ptr(a['A_t']),
+                                               ptr(a['b_t']), ptr(a['Q']), ptr(a['c']), ptr(a['H']), self.device,
+                                               ctypes.byref(h))
+        _lib.check(rc, 'program_create')
+        self.h = h
+        info = _lib.Info()
+        _lib.check(self.lib.ppgpu_program_info(self.h, ctypes.byref(info)), 'program_info')
+        self.W, self.mi, self.R0 = info.words, info.n_ineq, info.region_rows
+        self.use_gram, self.max_depth, self.sm_count = bool(info.use_gram), info.max_depth, info.sm_count
+        self.lp_columns = info.lp_columns
+        self.h2d_bytes = sum(v.nbytes for v in a.values() if isinstance(v, numpy.ndarray))
+        self.d2h_bytes = 0
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.lib.ppgpu_program_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- thin wrappers -------------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.tdev)
+
+    def root_level(self) -> torch.Tensor:
+        masks = self.empty((max(self.mi, 1), self.W), torch.int64)
+        cnt = ctypes.c_int64(0)
+        _lib.check(self.lib.ppgpu_root_level(self.h, masks.data_ptr(), ctypes.byref(cnt), self._stream()), 'root_level')
+        return masks[:cnt.value]
+
+    def level_eval(self, masks: torch.Tensor, k_act: int, status: Optional[torch.Tensor] = None, stages: int = 7,
+                   lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+        n = masks.shape[0]
+        if status is None:
+            status = torch.zeros((n,), dtype=torch.uint8, device=self.tdev)
+        hi = n if hi is None else hi
+        if hi > lo:
+            _lib.check(self.lib.ppgpu_level_eval(self.h, masks.data_ptr() + lo * self.W * 8, hi - lo, k_act,
+                                                 status.data_ptr() + lo, stages, self._stream()), 'level_eval')
+        return status
+
+    def select(self, status: torch.Tensor, bits: int, value: int) -> torch.Tensor:
+        n = status.shape[0]
+        if n == 0:
+            return self.empty((0,), torch.int64)
+        ws_bytes = self.lib.ppgpu_scan_workspace_bytes(n)
+        ws = self.empty(((ws_bytes + 7) // 8,), torch.int64)
+        idx = self.empty((n,), torch.int64)
+        cnt = ctypes.c_int64(0)
+        _lib.check(self.lib.ppgpu_level_select(self.h, status.data_ptr(), n, bits, value, idx.data_ptr(), ctypes.byref(cnt),
+                                               ws.data_ptr(), ws_bytes, self._stream()), 'level_select')
+        return idx[:cnt.value]
+
+    def emit(self, masks: torch.Tensor, sel: torch.Tensor, k_act: int, status: torch.Tensor):
+        ns = sel.shape[0]
+        N = self.n + self.n_eq + k_act
+        laws = self.empty((ns, N, self.t + 1), torch.float64)
+        rows = self.empty((ns, self.R0, self.t + 1), torch.float64)
+        flags = self.empty((ns, self.R0), torch.int32)
+        info = self.empty((ns, 4), torch.float64)
+        _lib.check(self.lib.ppgpu_regions_emit(self.h, masks.data_ptr(), sel.data_ptr(), ns, k_act, laws.data_ptr(),
+                                               rows.data_ptr(), flags.data_ptr(), info.data_ptr(), status.data_ptr(),
+                                               self._stream()), 'regions_emit')
+        return laws, rows, flags, info
+
+    def children(self, masks: torch.Tensor, feas_idx: torch.Tensor, k_act: int) -> torch.Tensor:
+        nf = feas_idx.shape[0]
+        if nf == 0:
+            return self.empty((0, self.W), torch.int64)
+        feas_masks = self.empty((nf, self.W), torch.int64)
+        survive = self.empty((nf, self.W), torch.int64)
+        offsets = self.empty((nf + 1,), torch.int64)
+        ws_bytes = self.lib.ppgpu_scan_workspace_bytes(nf)
+        ws = self.empty(((ws_bytes + 7) // 8,), torch.int64)
+        tot = ctypes.c_int64(0)
+        _lib.check(self.lib.ppgpu_children_count(self.h, masks.data_ptr(), feas_idx.data_ptr(), nf, k_act,
+                                                 feas_masks.data_ptr(), survive.data_ptr(), offsets.data_ptr(),
+                                                 ctypes.byref(tot), ws.data_ptr(), ws_bytes, self._stream()),
+                   'children_count')
+        out = self.empty((tot.value, self.W), torch.int64)
+        if tot.value:
+            _lib.check(self.lib.ppgpu_children_write(self.h, feas_masks.data_ptr(), survive.data_ptr(), offsets.data_ptr(),
+                                                     nf, out.data_ptr(), self._stream()), 'children_write')
+        return out
+
+    def counters(self, reset: bool = False) -> Dict[str, int]:
+        buf = (ctypes.c_uint64 * _lib.NUM_COUNTERS)()
+        _lib.check(self.lib.ppgpu_counters(self.h, buf, int(reset), self._stream()), 'counters')
+        return {name: int(buf[i]) for i, name in enumerate(_lib.COUNTER_NAMES)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.ppgpu_launch_count(self.h))
+
+    # ---- bitmask helpers (host side, small) ----------------------------------------------------------------------
+    def masks_from_lists(self, active_sets) -> torch.Tensor:
+        """uint64 bitmasks (as int64 tensor) for full active-set index lists [eq..., ineq...]."""
+        out = numpy.zeros((len(active_sets), self.W), dtype=numpy.uint64)
+        for ci, aset in enumerate(active_sets):
+            for idx in aset:
+                i = int(idx) - self.n_eq
+                if i >= 0:
+                    out[ci, i >> 6] |= numpy.uint64(1) << numpy.uint64(i & 63)
+        return torch.from_numpy(out.view(numpy.int64)).to(self.tdev)
+
+    def lists_from_masks(self, masks_np: numpy.ndarray) -> List[List[int]]:
+        eq = list(range(self.n_eq))
+        m = masks_np.view(numpy.uint64).reshape(-1, self.W)
+        bits = numpy.unpackbits(m.view(numpy.uint8).reshape(m.shape[0], -1), axis=1, bitorder='little')
+        return [eq + (numpy.nonzero(r)[0] + self.n_eq).tolist() for r in bits]
+
+
+def measure_fp64_peak(iters: int = 20000) -> float:
+    lib = _lib.load()
+    v = ctypes.c_double(0.0)
+    _lib.check(lib.ppgpu_measure_fp64_peak(iters, ctypes.byref(v), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               'fp64 peak')
+    return v.value
+
+
+def _region_classes(program):
+    """ppopt's own result classes when the program is a ppopt object, else this package's mirrors."""
+    mod = type(program).__module__
+    root = mod.split('.mpqp_program')[0].split('.mplp_program')[0]
+    if root not in ('ppopt_b200',) and root.endswith('ppopt'):
+        import importlib
+        try:
+            cr = importlib.import_module(root + '.critical_region').CriticalRegion
+            sol = importlib.import_module(root + '.solution').Solution
+            return cr, sol
+        except Exception:
+            pass
+    from .critical_region import CriticalRegion
+    from .solution import Solution
+    return CriticalRegion, Solution
+
+
+def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, info) -> list:
+    """CriticalRegion objects from K5's buffers (field meaning: mpqp_utils.py:181-195)."""
+    n, t, ne, m = eng.n, eng.t, eng.n_eq, eng.m
+    out = []
+    n_inact = eng.mi - k_act
+    for si, aset in enumerate(active_sets):
+        if info[si, 0] != 1.0:
+            out.append(None)
+            continue
+        law = laws[si]
+        fl = flags[si]
+        kept = numpy.nonzero((fl & 3) == 3)[0]
+        if t == 1:
+            E = numpy.array([[1], [-1]])
+            f = numpy.array([[info[si, 3]], [-info[si, 2]]])
+        else:
+            nd = numpy.nonzero(((fl & 3) == 3) & ((fl & 4) == 0))[0]
+            E = numpy.ascontiguousarray(rows[si][nd, 1:])
+            f = numpy.ascontiguousarray(rows[si][nd, :1])
+        active = aset[ne:]
+        aset_set = set(aset)
+        inactive = [i for i in range(m) if i not in aset_set]
+        lam = [active[i] for i in kept if i < k_act]
+        reg_pos = [int(i - k_act) for i in kept if k_act <= i < k_act + n_inact]
+        omega = [int(i - k_act - n_inact) for i in kept if i >= k_act + n_inact]
+        region = cr_cls(numpy.ascontiguousarray(law[:n, 1:]), numpy.ascontiguousarray(law[:n, :1]),
+                        numpy.ascontiguousarray(law[n:, 1:]), numpy.ascontiguousarray(law[n:, :1]), E, f, list(aset),
+                        omega, lam, [reg_pos, [inactive[p] for p in reg_pos]])
+        out.append(region)
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def solve(program, max_levels: Optional[int] = None, collect_status: bool = False, engine: Optional[Engine] = None,
+          emit_regions: bool = True, distributed: bool = True, expand_last: bool = False):
+    """GPU replacement for mpqp_combinatorial.solve(program) (mpqp_combinatorial.py:10-72).
+
+    Returns the Solution; per-level statistics are attached as ``solution.level_stats`` (candidates, feasible,
+    optimal-screen, regions, seconds) - the counters the reference's parallel solvers print
+    (mpqp_parrallel_combinatorial.py:103-104).  ``max_levels`` caps the depth for programs nobody can finish
+    (applied identically to the CPU baselines in bench.py).
+
+    Under torch.distributed (world size G > 1) every level's candidate array is cut into G contiguous slices, rank g
+    evaluates slice g, the status bytes are all-gathered (NCCL), and every rank then generates the identical next level.
+    """
+    own = engine is None
+    eng = Engine(program_arrays(program)) if own else engine
+    cr_cls, sol_cls = _region_classes(program)
+    dist = _dist() if distributed else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    regions: list = []
+    stats = []
+    statuses = []
+    depth = eng.max_depth if max_levels is None else min(eng.max_depth, max_levels)
+    complete = max_levels is None or max_levels >= eng.max_depth
+    masks = eng.root_level() if depth > 0 else eng.empty((0, eng.W), torch.int64)
+    total = 0
+    for lvl in range(depth):
+        n = masks.shape[0]
+        if n == 0:
+            break
+        t0 = time.perf_counter()
+        k_act = lvl + 1
+        status = torch.zeros((n,), dtype=torch.uint8, device=eng.tdev)
+        if world > 1:
+            per = (n + world - 1) // world
+            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            eng.level_eval(masks, k_act, status, 7, lo, hi)
+            padded = torch.zeros((per,), dtype=torch.uint8, device=eng.tdev)
+            padded[:hi - lo] = status[lo:hi]
+            gathered = torch.empty((per * world,), dtype=torch.uint8, device=eng.tdev)
+            dist.all_gather_into_tensor(gathered, padded)
+            status = gathered[:n].contiguous()
+        else:
+            eng.level_eval(masks, k_act, status, 7)
+        n_reg = 0
+        opt_idx = eng.select(status, ST_OPT, ST_OPT)
+        n_opt = int(opt_idx.shape[0])
+        if n_opt and emit_regions:
+            # regions are emitted by the rank that owns the candidate; rank 0 collects them at the end
+            if world > 1:
+                per = (n + world - 1) // world
+                mine = opt_idx[(opt_idx >= rank * per) & (opt_idx < (rank + 1) * per)].contiguous()
+            else:
+                mine = opt_idx
+            if mine.shape[0]:
+                laws, rows, flags, info = eng.emit(masks, mine, k_act, status)
+                sel_masks = masks[mine].cpu().numpy()
+                laws, rows, flags, info = laws.cpu().numpy(), rows.cpu().numpy(), flags.cpu().numpy(), info.cpu().numpy()
+                eng.d2h_bytes += laws.nbytes + rows.nbytes + flags.nbytes + info.nbytes + sel_masks.nbytes
+                asets = eng.lists_from_masks(sel_masks)
+                if numpy.any(info[:, 0] < 0):
+                    raise numpy.linalg.LinAlgError('Singular matrix')  # what the reference raises (mpqp_program.py:187)
+                built = [(int(i), r) for i, r in zip(mine.cpu().tolist(),
+                                                     build_regions(eng, cr_cls, asets, k_act, laws, rows, flags, info))
+                         if r is not None]
+            else:
+                built = []
+            if world > 1:
+                allb = [None] * world
+                dist.all_gather_object(allb, built)
+                built = sorted([x for part in allb for x in part], key=lambda x: x[0])
+            regions.extend(r for _, r in built)
+            n_reg = len(built)
+        feas_idx = eng.select(status, ST_FEAS, ST_FEAS)
+        n_feas = int(feas_idx.shape[0])
+        if collect_status:
+            statuses.append((masks.cpu().numpy(), status.cpu().numpy()))
+        last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
+        nxt = eng.children(masks, feas_idx, k_act) if not last else eng.empty((0, eng.W), torch.int64)
+        torch.cuda.synchronize(eng.tdev)
+        total += n
+        stats.append(dict(level=lvl + 1, candidates=n, feasible=n_feas, optimal=n_opt, regions=n_reg,
+                          seconds=time.perf_counter() - t0))
+        masks = nxt
+    frontier = int(masks.shape[0])
+    # base (equality-only) active set, tested last (mpqp_combinatorial.py:65-70)
+    base_status = 0
+    if complete:
+        m0 = torch.zeros((1, eng.W), dtype=torch.int64, device=eng.tdev)
+        st0 = eng.level_eval(m0, 0)
+        sel0 = eng.select(st0, ST_OPT, ST_OPT)
+        if sel0.shape[0] and emit_regions:
+            laws, rows, flags, info = [x.cpu().numpy() for x in eng.emit(m0, sel0, 0, st0)]
+            if info[0, 0] < 0:
+                raise numpy.linalg.LinAlgError('Singular matrix')
+            reg = build_regions(eng, cr_cls, [list(range(eng.n_eq))], 0, laws, rows, flags, info)[0]
+            # region.is_full_dimension(): Chebyshev radius of (E, f) > 1e-8 (critical_region.py:89-105)
+            if reg is not None and info[0, 1] > 1e-8:
+                regions.append(reg)
+        base_status = int(st0.cpu().numpy()[0])
+    solution = sol_cls(program, regions)
+    solution.level_stats = stats
+    solution.total_candidates = total
+    solution.frontier = frontier
+    solution.base_status = base_status
+    solution.engine_counters = eng.counters()
+    solution.gpu_launches = eng.launch_count()
+    solution.h2d_bytes, solution.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
+    if collect_status:
+        solution.level_status = statuses
+    if own:
+        eng.close()
+    return solution

@@ -1,0 +1,48 @@
+"""Dispatch with the reference's surface (/root/reference/src/ppopt/mp_solvers/solve_mpqp.py:23-114).
+
+Only the combinatorial algorithm is in scope (BASELINE.json north_star); the enum keeps the reference's member names so
+that calling code type-checks, and every other member raises NotImplementedError instead of silently returning an
+empty solution."""
+from enum import Enum
+
+import numpy
+
+from . import mpqp_combinatorial
+
+
+class mpqp_algorithm(Enum):
+    combinatorial = 'combinatorial'
+    combinatorial_parallel = 'p combinatorial'
+    combinatorial_parallel_exp = 'p combinatorial exp'
+    graph = 'graph'
+    graph_exp = 'graph exp'
+    graph_parallel = 'p graph'
+    graph_parallel_exp = 'p graph exp'
+    geometric = 'geometric'
+    geometric_parallel = 'p geometric'
+    geometric_parallel_exp = 'p geometric exp'
+    combinatorial_graph = 'combinatorial graph'
+
+    def __str__(self):
+        return self.name
+
+    @staticmethod
+    def all_algos():
+        return ''.join(f'mpqp_algorithm.{a}\n' for a in mpqp_algorithm)
+
+
+def solve_mpqp(problem, algorithm: mpqp_algorithm = mpqp_algorithm.combinatorial):
+    """Solves an mpQP or mpLP; same argument meaning and TypeError as the reference (solve_mpqp.py:52-66)."""
+    if not isinstance(algorithm, mpqp_algorithm):
+        raise TypeError("You must pass an algorithm from mpqp_algorithm as the continuous algorithm. These can be found "
+                        "by importing the following \n\nfrom ppopt_b200.mp_solvers.solve_mpqp import mpqp_algorithm\n\n"
+                        f"With the following choices\n{mpqp_algorithm.all_algos()}")
+    if algorithm is not mpqp_algorithm.combinatorial:
+        raise NotImplementedError(f'{algorithm} is outside the scope of the B200 engine (combinatorial only)')
+    solution = mpqp_combinatorial.solve(problem)
+    # overlap flags exactly as the reference sets them (solve_mpqp.py:105-112)
+    if hasattr(problem, 'Q') and problem.Q is not None:
+        if min(numpy.linalg.eigvalsh(problem.Q)) <= 0:
+            solution.is_overlapping = True
+    solution.is_overlapping = True  # isinstance(problem, MPLP_Program) holds for both program types in the reference
+    return solution

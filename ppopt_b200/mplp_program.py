@@ -1,0 +1,82 @@
+"""Program containers with the attribute surface the combinatorial path reads from the reference's
+MPLP_Program / MPQP_Program (/root/reference/src/ppopt/mplp_program.py:45-58,140-156; mpqp_program.py:15-42).
+
+Round-1 scope: these hold ALREADY PRESOLVED data (the arrays a reference program object has after its constructor ran:
+equalities first and renumbered 0..n_eq-1, theta-only rows moved to A_t, rows of [A|-F] L2-normalised, redundant rows
+removed).  The reference's presolve itself (process_constraints etc., one LP per row) is SURVEY.md section 8f row 1 and
+is not re-implemented yet; genuine ppopt program objects can be passed to the engine directly instead.
+"""
+from typing import List, Optional
+
+import numpy
+
+
+def _f64(a, cols=None):
+    a = numpy.ascontiguousarray(numpy.asarray(a, dtype=numpy.float64))
+    if a.ndim == 1:
+        a = a.reshape(-1, 1) if cols is None else a.reshape(-1, cols)
+    return a
+
+
+class MPLP_Program:
+    r"""min theta'H'x + c'x  s.t.  A x <= b + F theta (first n_eq rows equalities),  A_t theta <= b_t."""
+
+    def __init__(self, A, b, c, H, A_t, b_t, F, c_c=None, c_t=None, Q_t=None, equality_indices=None, solver=None,
+                 post_process=False):
+        if post_process:
+            raise NotImplementedError('presolve is not part of the round-1 scope: pass presolved arrays '
+                                      '(post_process=False) or a ppopt program object')
+        self.A, self.b, self.c, self.H = _f64(A), _f64(b), _f64(c), _f64(H)
+        self.A_t, self.b_t, self.F = _f64(A_t), _f64(b_t), _f64(F)
+        t = self.F.shape[1]
+        self.c_c = numpy.array([[0.0]]) if c_c is None else _f64(c_c)
+        self.c_t = numpy.zeros((t, 1)) if c_t is None else _f64(c_t)
+        self.Q_t = numpy.zeros((t, t)) if Q_t is None else _f64(Q_t)
+        eq = [] if equality_indices is None else [int(i) for i in equality_indices]
+        if eq != list(range(len(eq))):
+            raise ValueError('presolved programs have their equality rows first: equality_indices must be range(n_eq)')
+        self.equality_indices: List[int] = eq
+        self.solver = solver
+
+    def num_x(self) -> int:
+        return self.A.shape[1]
+
+    def num_t(self) -> int:
+        return self.F.shape[1]
+
+    def num_constraints(self) -> int:
+        return self.A.shape[0]
+
+    def num_inequality_constraints(self) -> int:
+        return self.A.shape[0] - len(self.equality_indices)
+
+    def num_equality_constraints(self) -> int:
+        return len(self.equality_indices)
+
+    def evaluate_objective(self, x, theta_point) -> float:
+        v = theta_point.T @ self.H.T @ x + self.c.T @ x + self.c_c + self.c_t.T @ theta_point \
+            + 0.5 * theta_point.T @ self.Q_t @ theta_point
+        return float(v[0, 0])
+
+
+class MPQP_Program(MPLP_Program):
+    r"""min 1/2 x'Qx + theta'H'x + c'x  with the constraints of MPLP_Program."""
+
+    def __init__(self, A, b, c, H, Q, A_t, b_t, F, c_c=None, c_t=None, Q_t=None, equality_indices=None, solver=None,
+                 post_process=False):
+        self.Q = _f64(Q)
+        super().__init__(A, b, c, H, A_t, b_t, F, c_c, c_t, Q_t, equality_indices, solver, post_process)
+
+    def evaluate_objective(self, x, theta_point) -> float:
+        v = 0.5 * x.T @ self.Q @ x + theta_point.T @ self.H.T @ x + self.c.T @ x + self.c_c \
+            + self.c_t.T @ theta_point + 0.5 * theta_point.T @ self.Q_t @ theta_point
+        return float(v[0, 0])
+
+
+def load_presolved(path: str):
+    """Program object from a tests/golden/*.npz fixture (post-presolve arrays written by oracle/gen_golden.py)."""
+    g = numpy.load(path)
+    eq = list(range(int(g['n_eq'])))
+    if str(g['kind']) == 'qp':
+        return MPQP_Program(g['A'], g['b'], g['c'], g['H'], g['Q'], g['A_t'], g['b_t'], g['F'], equality_indices=eq)
+    return MPLP_Program(g['A'], g['b'], g['c'], g['H'], g['A_t'], g['b_t'], g['F'], equality_indices=eq)
