@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const long lon
 
 size_t scan_workspace_bytes(long long n) {
     const long long nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 1;
-    return (size_t)(n + 1 + nb + 1) * sizeof(long long);
+    return (size_t)(n + 1 + nb + 2) * sizeof(long long);  // offsets, block sums (+ total), one result slot
 }
 
 // exclusive scan of vals[0..n) in place -> vals[0..n], vals[n] = total; bsum = scratch of nb+1
@@ -128,7 +128,7 @@ __global__ void select_scatter_kernel(const uint8_t* __restrict__ status, long l
 // ordered compaction: indices i with (status[i] & bits) == value, ascending; *d_count = how many
 cudaError_t select_indices(const uint8_t* status, long long n, uint8_t bits, uint8_t value, long long* idx_out,
                            long long* d_count, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (ws_bytes < scan_workspace_bytes(n)) return cudaErrorInvalidValue;
+    if (ws_bytes + sizeof(long long) < scan_workspace_bytes(n)) return cudaErrorInvalidValue;
     long long* offs = (long long*)ws;
     long long* bsum = offs + n + 1;
     if (n == 0) return cudaMemsetAsync(d_count, 0, sizeof(long long), st);
