@@ -12,7 +12,7 @@ from typing import Dict, List, Optional
 import numpy
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from ._lib import ST_FEAS, ST_OPT, ST_REGION
 
 
@@ -274,14 +274,9 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         k_act = lvl + 1
         status = torch.zeros((n,), dtype=torch.uint8, device=eng.tdev)
         if world > 1:
-            per = (n + world - 1) // world
-            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            lo, hi, _ = sharding.slice_bounds(n, rank, world)
             eng.level_eval(masks, k_act, status, 7, lo, hi)
-            padded = torch.zeros((per,), dtype=torch.uint8, device=eng.tdev)
-            padded[:hi - lo] = status[lo:hi]
-            gathered = torch.empty((per * world,), dtype=torch.uint8, device=eng.tdev)
-            dist.all_gather_into_tensor(gathered, padded)
-            status = gathered[:n].contiguous()
+            status = sharding.gather_status(status, n, dist, rank, world)
         else:
             eng.level_eval(masks, k_act, status, 7)
         n_reg = 0
@@ -289,11 +284,7 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         n_opt = int(opt_idx.shape[0])
         if n_opt and emit_regions:
             # regions are emitted by the rank that owns the candidate; rank 0 collects them at the end
-            if world > 1:
-                per = (n + world - 1) // world
-                mine = opt_idx[(opt_idx >= rank * per) & (opt_idx < (rank + 1) * per)].contiguous()
-            else:
-                mine = opt_idx
+            mine = sharding.owned(opt_idx, n, rank, world) if world > 1 else opt_idx
             if mine.shape[0]:
                 laws, rows, flags, info = eng.emit(masks, mine, k_act, status)
                 sel_masks = masks[mine].cpu().numpy()

@@ -1,0 +1,147 @@
+"""CPU tests of the host side: C ABI surface, pruning bookkeeping (reference tests mirrored), problem builders,
+argument validation, multi-process sharding over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from ppopt_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'ppgpu.h')).read()
+    declared = set(re.findall(r'\b(ppgpu_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ppgpu_version() >= 100
+    assert lib.ppgpu_scan_workspace_bytes(1000) >= 8 * 1001
+
+
+def test_abi_no_torch_types_in_header():
+    header = open(os.path.join(ROOT, 'include', 'ppgpu.h')).read()
+    assert 'torch' not in header.replace('torch tensor data_ptr', '') and 'at::' not in header
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'ppopt_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.hpp', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                code = '\n'.join(l for l in src.splitlines() if not l.lstrip().startswith(('//', '#', '*', '"""')))
+                assert 'ppopt_oracle' not in src and 'twin_binding' not in src and 'libtwin' not in src, f
+                assert not re.search(r'(import|include|from|CDLL).*oracle', code), f
+
+
+# ---- mirrored from the reference's tests/mpqp_solver_tests/test_mpqp_combinatorial.py:10-82
+def test_combination_tester_semantics():
+    from ppopt_b200.mp_solvers.solver_utils import CombinationTester, generate_children_sets
+    t = CombinationTester()
+    assert t.check([]) and t.check(set()) and t.check([1, 2, 3])
+    t.add_combo([1, 2])
+    assert not t.check([1, 2]) and not t.check([0, 1, 2, 5]) and t.check([1, 3]) and t.check({2})
+    t.add_combos({(4,), (0, 3)})
+    assert not t.check([4]) and not t.check([0, 1, 3]) and t.check([0, 1])
+    assert generate_children_sets([], 3) == [[0], [1], [2]]
+    assert generate_children_sets([1], 4) == [[1, 2], [1, 3]]
+    assert generate_children_sets([0, 1], 5, t) == [[0, 1, 2]][:0] + [c for c in [[0, 1, 2], [0, 1, 3], [0, 1, 4]] if t.check(c)]
+    assert generate_children_sets([3], 4) == []
+    t2 = CombinationTester()
+    t2.add_combo({1, 2})  # the reference ignores plain sets
+    assert t2.check([1, 2])
+
+
+def test_problem_builders_reproduce_reference_inputs():
+    from ppopt_b200 import problems
+    for name, build in problems.CONFIGS.items():
+        g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
+        raw = build()
+        for k in ('A', 'b', 'c', 'H', 'A_t', 'b_t', 'F'):
+            assert numpy.array_equal(numpy.asarray(raw[k], dtype=float), g['raw_' + k]), (name, k)
+        if raw['kind'] == 'qp':
+            assert numpy.array_equal(raw['Q'], g['raw_Q'])
+
+
+def test_program_arrays_validation():
+    from ppopt_b200 import engine
+    from ppopt_b200.mplp_program import MPQP_Program, load_presolved
+    p = load_presolved(os.path.join(GOLDEN, 'factory_mpqp.npz'))
+    a = engine.program_arrays(p)
+    assert a['is_qp'] and a['A'].flags.c_contiguous and a['b'].ndim == 1 and a['n_eq'] == 0
+    p.H = numpy.zeros((2, 4))  # transposed all-zero H is accepted (reference fixtures do this)
+    assert engine.program_arrays(p)['H'].shape == (4, 2)
+    p.H = numpy.ones((2, 4))
+    with pytest.raises(ValueError):
+        engine.program_arrays(p)
+    with pytest.raises(ValueError):
+        MPQP_Program(p.A, p.b, p.c, numpy.zeros((4, 2)), p.Q, p.A_t, p.b_t, p.F, equality_indices=[1])
+    lp = load_presolved(os.path.join(GOLDEN, 'transport_mplp.npz'))
+    assert not engine.program_arrays(lp)['is_qp']
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from ppopt_b200 import solve_mpqp
+    from ppopt_b200.mplp_program import load_presolved
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        solve_mpqp(load_presolved(os.path.join(GOLDEN, 'factory_mpqp.npz')))
+
+
+def test_slice_bounds_cover_exactly():
+    from ppopt_b200.sharding import slice_bounds
+    for n in (0, 1, 5, 16, 17, 1000):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi, per = slice_bounds(n, r, world)
+                assert 0 <= lo <= hi <= n and hi - lo <= per
+                seen.extend(range(lo, hi))
+            assert seen == list(range(n))
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], 'oracle'))
+import numpy, torch, torch.distributed as dist
+from ppopt_b200 import sharding
+import twin_binding
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+path = os.path.join(sys.argv[1], 'tests', 'golden', 'mpc_n3.npz')
+g = numpy.load(path); tw = twin_binding.Twin.from_npz(path)
+for lv in range(int(g['n_levels'])):
+    cands = g[f'level{lv}_candidates']; n = len(cands)
+    lo, hi, per = sharding.slice_bounds(n, rank, world)
+    status = torch.zeros(n, dtype=torch.uint8)
+    if hi > lo:
+        status[lo:hi] = torch.from_numpy(tw.eval(tw.masks(cands[lo:hi].tolist())))
+    full = sharding.gather_status(status, n, dist, rank, world)
+    assert numpy.array_equal(full.numpy() & 11, g[f'level{lv}_status'] & 11), (rank, lv)
+    idx = torch.nonzero(full & 8).flatten()
+    mine = sharding.owned(idx, n, rank, world)
+    allm = [None, None]; dist.all_gather_object(allm, mine.tolist())
+    assert sorted(allm[0] + allm[1]) == idx.tolist()
+dist.barrier(); dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_level_sharding_world_size_2_gloo(tmp_path):
+    """N>1 host path on CPU: each rank evaluates its slice (CPU checker standing in for the kernels), status bytes
+    are all-gathered over gloo, every rank ends with the reference's full status vector."""
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
