@@ -104,6 +104,13 @@ int ppgpu_counters(ppgpu_program* prog, uint64_t* h_out, int32_t reset, ppgpu_st
 /* how many kernels this library has launched on behalf of the handle since creation */
 int64_t ppgpu_launch_count(const ppgpu_program* prog);
 
+/* Optional per-kernel-family timing with CUDA events recorded on the launch stream (used by bench.py for the
+ * roofline line).  Families: 0 K1 rank, 1 K2 feasibility LP, 2 K3/K4 screen, 3 K5 emission, 4 K6 count, 5 K6 write,
+ * 6 ordered compaction.  h_ms / h_launches hold PPGPU_NUM_FAMILIES entries. */
+#define PPGPU_NUM_FAMILIES 8
+int ppgpu_profile_enable(ppgpu_program* prog, int32_t on);
+int ppgpu_profile_read(ppgpu_program* prog, double* h_ms, int64_t* h_launches, int32_t reset);
+
 /* register-resident DFMA loop over all SMs: the FP64 roofline denominator, in TFLOP/s */
 int ppgpu_measure_fp64_peak(int32_t iters, double* h_tflops, ppgpu_stream stream);
 

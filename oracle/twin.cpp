@@ -115,27 +115,22 @@ LpResult lp_maxmin(Lp& lp, double thr, bool strict) {
         }
         if (j < 0) return {PPG_LP_OPTIMAL, beta};
         const double dir = (lp.colkind[j] == 1 && alpha[j] > 0.0) ? -1.0 : 1.0;
-        // ratio test (Harris two-pass; Bland: smallest basic variable among exact-min ties)
-        double tmax = INFINITY;
+        // ratio test: smallest rhs/a over rows with a > PPG_PIV_TOL; ties -> largest pivot, then smallest row
+        // (Bland mode: ties -> smallest basic variable id)
+        double tmin = INFINITY;
         for (int i = 0; i < nr; ++i) {
             if (lp.rowflag[i] != 1) continue;
             const double a = dir * lp.at(i, j);
-            if (a > PPG_PIV_TOL) {
-                const double rhs = std::fmax(lp.at(i, 0), 0.0);
-                tmax = std::fmin(tmax, (rhs + PPG_HARRIS) / a);
-            }
+            if (a > PPG_PIV_TOL) tmin = std::fmin(tmin, std::fmax(lp.at(i, 0), 0.0) * (1.0 / a));
         }
-        if (tmax == INFINITY) return {PPG_LP_UNBOUNDED, INFINITY};
+        if (tmin == INFINITY) return {PPG_LP_UNBOUNDED, INFINITY};
         int r = -1; double bpiv = 0.0; int bvar = 1 << 30;
         for (int i = 0; i < nr; ++i) {
             if (lp.rowflag[i] != 1) continue;
             const double a = dir * lp.at(i, j);
-            if (a > PPG_PIV_TOL) {
-                const double rhs = std::fmax(lp.at(i, 0), 0.0);
-                if (rhs / a <= tmax) {
-                    if (bland) { if (lp.bvar[i] < bvar) { bvar = lp.bvar[i]; r = i; } }
-                    else if (a > bpiv) { bpiv = a; r = i; }
-                }
+            if (a > PPG_PIV_TOL && std::fmax(lp.at(i, 0), 0.0) * (1.0 / a) <= tmin) {
+                if (bland) { if (lp.bvar[i] < bvar) { bvar = lp.bvar[i]; r = i; } }
+                else if (a > bpiv) { bpiv = a; r = i; }
             }
         }
         const double step = std::fmax(lp.at(r, 0), 0.0) / (dir * lp.at(r, j));

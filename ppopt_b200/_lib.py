@@ -7,6 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libppgpu.so')
 
 NUM_COUNTERS = 16
+NUM_FAMILIES = 8
+FAMILY_NAMES = ('k1_rank', 'k2_feas_lp', 'k34_kkt_cheb', 'k5_emit', 'k6_count', 'k6_write', 'select', 'other')
 COUNTER_NAMES = ('k1_candidates', 'k2_lps', 'k2_pivots', 'k2_work', 'k4_lps', 'k4_pivots', 'k4_work', 'k5_lps',
                  'k5_pivots', 'k5_work', 'numeric', 'border', 'k6_lookups')
 
@@ -40,6 +42,8 @@ SYMBOLS = {
     'ppgpu_children_write': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'ppgpu_counters': (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     'ppgpu_launch_count': (_i64, [_vp]),
+    'ppgpu_profile_enable': (ctypes.c_int, [_vp, _i32]),
+    'ppgpu_profile_read': (ctypes.c_int, [_vp, _vp, _vp, _i32]),
     'ppgpu_measure_fp64_peak': (ctypes.c_int, [_i32, ctypes.POINTER(ctypes.c_double), _vp]),
 }
 

@@ -23,6 +23,27 @@ struct ppgpu_program {
     unsigned long long* d_queue = nullptr;     // work-queue heads, one per launch in flight
     int queue_slot = 0;
     long long launches = 0;
+    // optional per-family kernel timing (CUDA events on the launch stream)
+    bool profiling = false;
+    struct Span { int family; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[PPGPU_NUM_FAMILIES] = {0};
+    long long prof_launches[PPGPU_NUM_FAMILIES] = {0};
+};
+
+struct ProfScope {
+    ppgpu_program* p; cudaStream_t st; int family; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(ppgpu_program* p) {
+        if (!p->event_pool.empty()) { cudaEvent_t e = p->event_pool.back(); p->event_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ProfScope(ppgpu_program* p_, cudaStream_t st_, int fam) : p(p_), st(st_), family(fam) {
+        if (p->profiling) { a = get(p); b = get(p); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, st); p->spans.push_back({family, a, b}); }
+    }
 };
 
 static const int QUEUE_SLOTS = 64;
@@ -101,6 +122,8 @@ int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, 
 int ppgpu_program_destroy(ppgpu_program* p) {
     if (!p) return 0;
     for (void* d : p->allocs) cudaFree(d);
+    for (auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     delete p;
     return 0;
 }
@@ -133,16 +156,19 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (stages & 1) {
+        ProfScope ps(p, st, 0);
         e = launch_k1(p->dev, d_masks, n, k_act, d_status, p->d_counters, p->sm_count, st);
         if (e != cudaSuccess) return fail("K1 rank", e);
         p->launches++;
     }
     if (stages & 2) {
+        ProfScope ps(p, st, 1);
         e = launch_k2(p->dev, d_masks, n, d_status, next_queue(p, st), p->d_counters, p->sm_count, st);
         if (e != cudaSuccess) return fail("K2 feasibility", e);
         p->launches++;
     }
     if (stages & 4) {
+        ProfScope ps(p, st, 2);
         if (p->dev.is_qp && p->dev.use_gram) {
             e = launch_k34(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st);
         } else {
@@ -165,8 +191,11 @@ int ppgpu_level_select(ppgpu_program* p, const uint8_t* d_status, int64_t n, uin
     // the count lands in the last workspace word, then comes back to the host
     if (ws_bytes < scan_workspace_bytes(n)) return fail_msg("workspace too small");
     long long* d_count = (long long*)d_ws + (scan_workspace_bytes(n) / sizeof(long long) - 1);
-    cudaError_t e = select_indices(d_status, n, bits, value, (long long*)d_idx_out, d_count, d_ws,
-                                   ws_bytes - sizeof(long long), st);
+    cudaError_t e;
+    {
+        ProfScope ps(p, st, 6);
+        e = select_indices(d_status, n, bits, value, (long long*)d_idx_out, d_count, d_ws, ws_bytes - sizeof(long long), st);
+    }
     if (e != cudaSuccess) return fail("select", e);
     p->launches += 5;
     long long cnt = 0;
@@ -182,8 +211,12 @@ int ppgpu_regions_emit(ppgpu_program* p, const uint64_t* d_masks, const int64_t*
                        ppgpu_stream stream) {
     if (!p) return fail_msg("null argument");
     if (n_sel <= 0) return 0;
-    cudaError_t e = launch_k5(p->dev, d_masks, (const long long*)d_sel, n_sel, k_act, d_laws, d_rows, d_flags, d_info,
-                              d_status, p->d_counters, p->sm_count, (cudaStream_t)stream);
+    cudaError_t e;
+    {
+        ProfScope ps(p, (cudaStream_t)stream, 3);
+        e = launch_k5(p->dev, d_masks, (const long long*)d_sel, n_sel, k_act, d_laws, d_rows, d_flags, d_info, d_status,
+                      p->d_counters, p->sm_count, (cudaStream_t)stream);
+    }
     if (e != cudaSuccess) return fail("K5 emit", e);
     p->launches++;
     return 0;
@@ -196,8 +229,12 @@ int ppgpu_children_count(ppgpu_program* p, const uint64_t* d_masks, const int64_
     *h_total = 0;
     if (nf <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = children_count(p->dev, d_masks, (const long long*)d_feas_idx, nf, k_act, d_feas_masks, d_survive,
-                                   (long long*)d_offsets, d_ws, ws_bytes, p->d_counters, st);
+    cudaError_t e;
+    {
+        ProfScope ps(p, st, 4);
+        e = children_count(p->dev, d_masks, (const long long*)d_feas_idx, nf, k_act, d_feas_masks, d_survive,
+                           (long long*)d_offsets, d_ws, ws_bytes, p->d_counters, st);
+    }
     if (e != cudaSuccess) return fail("K6 count", e);
     p->launches += 5;
     long long tot = 0;
@@ -211,8 +248,11 @@ int ppgpu_children_count(ppgpu_program* p, const uint64_t* d_masks, const int64_
 int ppgpu_children_write(ppgpu_program* p, const uint64_t* d_feas_masks, const uint64_t* d_survive,
                          const int64_t* d_offsets, int64_t nf, uint64_t* d_children, ppgpu_stream stream) {
     if (!p) return fail_msg("null argument");
-    cudaError_t e = children_write(p->dev, d_feas_masks, d_survive, (const long long*)d_offsets, nf, d_children,
-                                   (cudaStream_t)stream);
+    cudaError_t e;
+    {
+        ProfScope ps(p, (cudaStream_t)stream, 5);
+        e = children_write(p->dev, d_feas_masks, d_survive, (const long long*)d_offsets, nf, d_children, (cudaStream_t)stream);
+    }
     if (e != cudaSuccess) return fail("K6 write", e);
     p->launches += nf > 0;
     return 0;
@@ -229,6 +269,30 @@ int ppgpu_counters(ppgpu_program* p, uint64_t* h_out, int32_t reset, ppgpu_strea
 }
 
 int64_t ppgpu_launch_count(const ppgpu_program* p) { return p ? p->launches : 0; }
+
+int ppgpu_profile_enable(ppgpu_program* p, int32_t on) {
+    if (!p) return fail_msg("null argument");
+    p->profiling = on != 0;
+    return 0;
+}
+
+int ppgpu_profile_read(ppgpu_program* p, double* h_ms, int64_t* h_launches, int32_t reset) {
+    if (!p || !h_ms || !h_launches) return fail_msg("null argument");
+    for (auto& s : p->spans) {
+        cudaError_t e = cudaEventSynchronize(s.b);
+        if (e != cudaSuccess) return fail("profile sync", e);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        p->prof_ms[s.family] += ms;
+        p->prof_launches[s.family] += 1;
+        p->event_pool.push_back(s.a);
+        p->event_pool.push_back(s.b);
+    }
+    p->spans.clear();
+    for (int f = 0; f < PPGPU_NUM_FAMILIES; ++f) { h_ms[f] = p->prof_ms[f]; h_launches[f] = p->prof_launches[f]; }
+    if (reset) for (int f = 0; f < PPGPU_NUM_FAMILIES; ++f) { p->prof_ms[f] = 0; p->prof_launches[f] = 0; }
+    return 0;
+}
 
 int ppgpu_measure_fp64_peak(int32_t iters, double* h_tflops, ppgpu_stream stream) {
     if (!h_tflops) return fail_msg("null argument");

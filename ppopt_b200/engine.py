@@ -157,6 +157,15 @@ class Engine:
         _lib.check(self.lib.ppgpu_counters(self.h, buf, int(reset), self._stream()), 'counters')
         return {name: int(buf[i]) for i, name in enumerate(_lib.COUNTER_NAMES)}
 
+    def profile(self, on: bool):
+        _lib.check(self.lib.ppgpu_profile_enable(self.h, int(on)), 'profile_enable')
+
+    def profile_read(self, reset: bool = False) -> Dict[str, Dict]:
+        ms = (ctypes.c_double * _lib.NUM_FAMILIES)()
+        ln = (ctypes.c_int64 * _lib.NUM_FAMILIES)()
+        _lib.check(self.lib.ppgpu_profile_read(self.h, ms, ln, int(reset)), 'profile_read')
+        return {name: dict(ms=float(ms[i]), launches=int(ln[i])) for i, name in enumerate(_lib.FAMILY_NAMES)}
+
     def launch_count(self) -> int:
         return int(self.lib.ppgpu_launch_count(self.h))
 
@@ -243,7 +252,8 @@ def _dist():
 
 
 def solve(program, max_levels: Optional[int] = None, collect_status: bool = False, engine: Optional[Engine] = None,
-          emit_regions: bool = True, distributed: bool = True, expand_last: bool = False):
+          emit_regions: bool = True, distributed: bool = True, expand_last: bool = False,
+          materialize: bool = True):
     """GPU replacement for mpqp_combinatorial.solve(program) (mpqp_combinatorial.py:10-72).
 
     Returns the Solution; per-level statistics are attached as ``solution.level_stats`` (candidates, feasible,
@@ -285,7 +295,10 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         if n_opt and emit_regions:
             # regions are emitted by the rank that owns the candidate; rank 0 collects them at the end
             mine = sharding.owned(opt_idx, n, rank, world) if world > 1 else opt_idx
-            if mine.shape[0]:
+            if mine.shape[0] and not materialize:
+                eng.emit(masks, mine, k_act, status)  # results stay in HBM (device-resident throughput runs)
+                built = [(int(i), None) for i in range(int(mine.shape[0]))]
+            elif mine.shape[0]:
                 laws, rows, flags, info = eng.emit(masks, mine, k_act, status)
                 sel_masks = masks[mine].cpu().numpy()
                 laws, rows, flags, info = laws.cpu().numpy(), rows.cpu().numpy(), flags.cpu().numpy(), info.cpu().numpy()
@@ -302,7 +315,7 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
                 allb = [None] * world
                 dist.all_gather_object(allb, built)
                 built = sorted([x for part in allb for x in part], key=lambda x: x[0])
-            regions.extend(r for _, r in built)
+            regions.extend(r for _, r in built if r is not None)
             n_reg = len(built)
         feas_idx = eng.select(status, ST_FEAS, ST_FEAS)
         n_feas = int(feas_idx.shape[0])
