@@ -13,8 +13,16 @@
 
 namespace ppgpu {
 
+// resident CTAs per SM the register allocator is asked to make room for: the tableau needs 2*RPT*DC registers per
+// thread, ~48 more for everything else; more resident LPs hide the barrier / redux latency of a pivot
+constexpr int k2_min_blocks(int threads, int rpt, int dc) {
+    const int need = 2 * rpt * dc + 48;
+    const int mb = 65536 / (threads * need);
+    return mb < 1 ? 1 : (mb > 16 ? 16 : mb);
+}
+
 template <int NW, int RPT, int DC, int WPC>
-__global__ void __launch_bounds__(NW * 32 * WPC)
+__global__ void __launch_bounds__(NW * 32 * WPC, k2_min_blocks(NW * 32 * WPC, RPT, DC))
 k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, uint8_t* __restrict__ status,
                unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters) {
     typedef LpCore<NW, RPT, DC> Core;

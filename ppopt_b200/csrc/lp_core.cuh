@@ -92,14 +92,32 @@ __device__ __forceinline__ int warp_min_int(int v) {
     return v;
 }
 
+// min / max of NON-NEGATIVE doubles across a warp with two 32-bit redux.sync each (the IEEE order of non-negative
+// doubles is the unsigned order of their bit patterns); ~6 instructions instead of a 5-step shuffle ladder
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(PPG_FULL, hi);
+    const unsigned ml = __reduce_min_sync(PPG_FULL, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(PPG_FULL, hi);
+    const unsigned ml = __reduce_max_sync(PPG_FULL, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
 template <int NW, int DC>
 struct LpShared {
-    double P[DC];           // published pivot row (entry of the pivot column already replaced by 1)
-    double pinfo[2];        // effective pivot element, rhs of the pivot row
-    double red_v[3][NW];    // cross-warp reduction scratch, one slot per reduction site
-    int red_i[3][NW];
-    int nbvar[DC];          // variable id of each nonbasic column (Bland's rule)
-    unsigned char kind[DC]; // 0 dead, 1 free, 2 slack
+    double P[2][NW][DC];    // candidate pivot rows, one per warp, ping-pong over iterations (pivot-column entry := 1)
+    double c_ratio[2][NW];  // per-warp ratio-test winner: step length, effective pivot, rhs, row, basic-variable id
+    double c_piv[2][NW];
+    double c_rhs[2][NW];
+    int c_row[2][NW];
+    int c_bvar[2][NW];
+    double pinfo[2];        // phase A/B: pivot element
+    double red_v[2][NW];    // phase A/B cross-warp reduction scratch
+    int red_i[2][NW];
 };
 
 struct LpOut {
@@ -119,7 +137,7 @@ struct LpCore {
         if constexpr (NW == 1) __syncwarp(); else __syncthreads();
     }
 
-    // group-wide argmin / argmax / int-min, result known to every thread. `site` selects the scratch slot.
+    // group-wide argmin / int-min (phase A/B only), result known to every thread. `site` selects the scratch slot.
     __device__ __forceinline__ static void group_argmin(Shared& sh, int site, int warp, int lane, double& v, int& i) {
         warp_argmin(v, i);
         if constexpr (NW > 1) {
@@ -133,21 +151,8 @@ struct LpCore {
             }
         }
     }
-    __device__ __forceinline__ static void group_argmax(Shared& sh, int site, int warp, int lane, double& v, int& i) {
-        warp_argmax(v, i);
-        if constexpr (NW > 1) {
-            if (lane == 0) { sh.red_v[site][warp] = v; sh.red_i[site][warp] = i; }
-            __syncthreads();
-            v = sh.red_v[site][0]; i = sh.red_i[site][0];
-#pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const double ov = sh.red_v[site][w]; const int oi = sh.red_i[site][w];
-                if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-            }
-        }
-    }
     __device__ __forceinline__ static int group_min_int(Shared& sh, int site, int warp, int lane, int v) {
-        v = warp_min_int(v);
+        v = __reduce_min_sync(PPG_FULL, v);
         if constexpr (NW > 1) {
             if (lane == 0) sh.red_i[site][warp] = v;
             __syncthreads();
@@ -158,43 +163,29 @@ struct LpCore {
         return v;
     }
 
-    // owner of row r copies it (raw) to shared memory
-    __device__ __forceinline__ static void publish_row(Shared& sh, const double (&T)[RPT][DC], int tid, int r) {
-        if (tid == r % GT) {
-            const int slot = r / GT;
-            static_for<RPT>([&](auto RR) {
-                constexpr int rr = decltype(RR)::value;
-                if (rr == slot) {
-#pragma unroll
-                    for (int c = 0; c < DC; ++c) sh.P[c] = T[rr][c];
-                }
-            });
-        }
-    }
-
-    // Gauss-Jordan step on column j with the published row sh.P (sh.P[j] must already be 1, inv = 1/pivot).
+    // Gauss-Jordan step on column j with the published row P (P[j] == 1, inv = 1/pivot); colv[rr] = dir * T[rr][j].
     // Rows with rflag != 0 other than r are eliminated; row r is rescaled if it stays in the basis.
-    __device__ __forceinline__ static void eliminate(const Shared& sh, double (&T)[RPT][DC], const int (&rflag)[RPT], int tid,
-                                                     int r, int j, double inv, double dir, bool row_stays) {
+    __device__ __forceinline__ static void eliminate(const double* __restrict__ P, double (&T)[RPT][DC], const int (&rflag)[RPT],
+                                                     const double (&colv)[RPT], int tid, int r, int j, double inv, bool row_stays) {
         static_for<RPT>([&](auto RR) {
             constexpr int rr = decltype(RR)::value;
             const int row = rr * GT + tid;
             if (row == r) {
                 if (row_stays) {
 #pragma unroll
-                    for (int c = 0; c < DC; ++c) T[rr][c] = sh.P[c] * inv;
+                    for (int c = 0; c < DC; ++c) T[rr][c] = P[c] * inv;
                 }
             } else if (rflag[rr] != 0) {
-                const double f = dir * reg_pick<DC>(T[rr], j) * inv;
+                const double f = colv[rr] * inv;
                 reg_zero<DC>(T[rr], j);
 #pragma unroll
-                for (int c = 0; c < DC; ++c) T[rr][c] = fma(-f, sh.P[c], T[rr][c]);
+                for (int c = 0; c < DC; ++c) T[rr][c] = fma(-f, P[c], T[rr][c]);
             }
         });
     }
 
     // Solves the LP held in registers. On entry: T rows, rflag (0 dead / 1 inequality / 2 equality), ncol = number
-    // of nonbasic columns (columns 1..ncol, the last one, js = ncol, is s), sh.kind/sh.nbvar are initialised here.
+    // of nonbasic columns (columns 1..ncol, the last one, js = ncol, is s).
     // Returns (uniformly on all threads) once beta >= thr (strict: beta > thr), at optimality, or on failure.
     __device__ static LpOut solve(Shared& sh, double (&T)[RPT][DC], int (&rflag)[RPT], int nrows, int ncol, double thr,
                                   bool strict, int tid) {
@@ -205,24 +196,20 @@ struct LpCore {
             constexpr int rr = decltype(RR)::value;
             bvar[rr] = DC + rr * GT + tid;
         });
-        for (int c = tid; c < DC; c += GT) {
-            sh.kind[c] = (c >= 1 && c <= ncol) ? 1 : 0;
-            sh.nbvar[c] = c;
+        // column kinds (0 dead, 1 free, 2 slack) and variable ids, replicated lane-wise in every warp
+        int kind[CPL], nbv[CPL];
+        double alpha[CPL];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            const int c = cc * 32 + lane;
+            kind[cc] = (c >= 1 && c <= ncol) ? 1 : 0;
+            nbv[cc] = c;
+            alpha[cc] = 0.0;
         }
         LpOut out;
         out.code = PPG_LP_OPTIMAL; out.beta = -CUDART_INF; out.pivots = 0; out.work = 0;
-        int live = 0;
-        {
-            int cnt = 0;
-            static_for<RPT>([&](auto RR) {
-                constexpr int rr = decltype(RR)::value;
-                cnt += rflag[rr] != 0;
-            });
-            // live-row count only feeds the work counter; a warp-level sum is enough precision for NW == 1 and
-            // for NW > 1 we simply use nrows (upper bound on useful work is not claimed anywhere)
-            live = nrows;
-            (void)cnt;
-        }
+        int live = nrows;
+        double* P0 = &sh.P[0][0][0];
         gsync();
         // ---------------- Phase A: pivot the equality rows out (their slack is fixed at zero) ----------------
         for (;;) {
@@ -233,21 +220,33 @@ struct LpCore {
             });
             e = group_min_int(sh, 0, warp, lane, e);
             if (e == 0x7fffffff) break;
-            publish_row(sh, T, tid, e);
+            if (tid == e % GT) {
+                static_for<RPT>([&](auto RR) {
+                    constexpr int rr = decltype(RR)::value;
+                    if (rr == e / GT) {
+#pragma unroll
+                        for (int c = 0; c < DC; ++c) P0[c] = T[rr][c];
+                    }
+                });
+            }
             gsync();
             // largest free coefficient of the row (every warp finds it redundantly)
-            double best = 0.0; int j = 0x7fffffff;
+            double best = 0.0;
 #pragma unroll
             for (int cc = 0; cc < CPL; ++cc) {
                 const int c = cc * 32 + lane;
-                if (c < DC && c != js && sh.kind[c] == 1) {
-                    const double a = fabs(sh.P[c]);
-                    if (a > best) { best = a; j = c; }
-                }
+                if (c < DC && c != js && kind[cc] == 1) best = fmax(best, fabs(P0[c]));
             }
-            warp_argmax(best, j);
-            const double rhs_e = sh.P[0];
-            if (j == 0x7fffffff || best < PPG_PIV_TOL) {
+            const double wbest = warp_max_nonneg(best);
+            int j = 0x7fffffff;
+#pragma unroll
+            for (int cc = 0; cc < CPL; ++cc) {
+                const int c = cc * 32 + lane;
+                if (c < DC && c != js && kind[cc] == 1 && fabs(P0[c]) == wbest) j = min(j, c);
+            }
+            j = __reduce_min_sync(PPG_FULL, j);
+            const double rhs_e = P0[0];
+            if (j == 0x7fffffff || wbest < PPG_PIV_TOL) {
                 if (fabs(rhs_e) > PPG_FEAS_TOL) { out.code = PPG_LP_INFEAS_EQ; return out; }
                 static_for<RPT>([&](auto RR) {
                     constexpr int rr = decltype(RR)::value;
@@ -256,20 +255,27 @@ struct LpCore {
                 gsync();
                 continue;
             }
-            const double piv = sh.P[j];
-            gsync();  // everyone has read P[j] before it is overwritten with 1
-            if (tid == 0) { sh.P[j] = 1.0; sh.kind[j] = 0; }
+            const double piv = P0[j];
+            double colv[RPT];
+            static_for<RPT>([&](auto RR) {
+                constexpr int rr = decltype(RR)::value;
+                colv[rr] = reg_pick<DC>(T[rr], j);
+            });
+            gsync();  // everyone has read P0[j] before it is overwritten with 1
+            if (tid == 0) P0[j] = 1.0;
             gsync();
-            eliminate(sh, T, rflag, tid, e, j, 1.0 / piv, 1.0, false);
+            eliminate(P0, T, rflag, colv, tid, e, j, 1.0 / piv, false);
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 if (rr * GT + tid == e) rflag[rr] = 0;
             });
+#pragma unroll
+            for (int cc = 0; cc < CPL; ++cc)
+                if (cc * 32 + lane == j) kind[cc] = 0;
             out.pivots++; out.work += (long long)live * (ncol + 1); live--;
             gsync();
         }
         // ---------------- Phase B: s enters the basis on the row of smallest rhs ----------------
-        double alpha[CPL];
         {
             double mn = CUDART_INF; int r0 = 0x7fffffff;
             static_for<RPT>([&](auto RR) {
@@ -282,25 +288,31 @@ struct LpCore {
             });
             group_argmin(sh, 1, warp, lane, mn, r0);
             if (r0 == 0x7fffffff) { out.code = PPG_LP_UNBOUNDED; out.beta = CUDART_INF; return out; }
+            double colv[RPT];
+            static_for<RPT>([&](auto RR) {
+                constexpr int rr = decltype(RR)::value;
+                colv[rr] = reg_pick<DC>(T[rr], js);
+            });
             if (tid == r0 % GT) {
                 static_for<RPT>([&](auto RR) {
                     constexpr int rr = decltype(RR)::value;
                     if (rr == r0 / GT) {
 #pragma unroll
-                        for (int c = 0; c < DC; ++c) sh.P[c] = T[rr][c];
-                        sh.pinfo[0] = reg_pick<DC>(T[rr], js);
+                        for (int c = 0; c < DC; ++c) P0[c] = T[rr][c];
+                        sh.pinfo[0] = colv[rr];
                     }
                 });
-                sh.P[js] = 1.0; sh.kind[js] = 2; sh.nbvar[js] = DC + r0;
+                P0[js] = 1.0;
             }
             gsync();
             const double inv = 1.0 / sh.pinfo[0];
 #pragma unroll
             for (int cc = 0; cc < CPL; ++cc) {
                 const int c = cc * 32 + lane;
-                alpha[cc] = (c < DC) ? sh.P[c] * inv : 0.0;
+                alpha[cc] = (c < DC) ? P0[c] * inv : 0.0;
+                if (c == js) { kind[cc] = 2; nbv[cc] = DC + r0; }
             }
-            eliminate(sh, T, rflag, tid, r0, js, inv, 1.0, false);
+            eliminate(P0, T, rflag, colv, tid, r0, js, inv, false);
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 if (rr * GT + tid == r0) rflag[rr] = 0;
@@ -308,103 +320,126 @@ struct LpCore {
             out.pivots++; out.work += (long long)live * (ncol + 1); live--;
             gsync();
         }
-        // ---------------- Phase C: primal simplex on the objective "s" ----------------
+        // ---------------- Phase C: primal simplex on the objective "s", ONE barrier per pivot ----------------
         int degen = 0; bool bland = false;
         const int cap = 50 * (nrows + ncol) + 200;
+        int buf = 0;
         for (int it = 0;; ++it) {
             const double beta = shfl_d(alpha[0], 0);
             out.beta = beta;
             if (strict ? (beta > thr) : (beta >= thr)) { out.code = PPG_LP_EARLY; return out; }
             if (it > cap) { out.code = PPG_LP_ITERLIM; return out; }
-            // pricing (lane-parallel over columns, replicated in every warp)
-            double best = PPG_OPT_TOL; int j = 0x7fffffff; int bestvar = 0x7fffffff;
+            // ---- pricing: lanes over columns, identical in every warp (no communication between warps)
+            int j;
+            if (!bland) {
+                double sc = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < CPL; ++cc) {
-                const int c = cc * 32 + lane;
-                if (c >= 1 && c <= ncol) {
-                    const int kd = sh.kind[c];
-                    double score = -1.0;
-                    if (kd == 1) score = fabs(alpha[cc]); else if (kd == 2) score = -alpha[cc];
-                    if (score > PPG_OPT_TOL) {
-                        if (bland) {
-                            const int vid = sh.nbvar[c];
-                            if (vid < bestvar) { bestvar = vid; j = c; }
-                        } else if (score > best) { best = score; j = c; }
-                    }
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const double s1 = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
+                    sc = fmax(sc, s1);
                 }
-            }
-            if (bland) {
-                // smallest variable id wins; carry the column along
-                int key = bestvar;
+                const double wsc = warp_max_nonneg(fmax(sc, 0.0));
+                if (!(wsc > PPG_OPT_TOL)) { out.code = PPG_LP_OPTIMAL; return out; }
+                j = 0x7fffffff;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int ok = __shfl_xor_sync(PPG_FULL, key, o);
-                    const int oj = __shfl_xor_sync(PPG_FULL, j, o);
-                    if (ok < key) { key = ok; j = oj; }
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const double s1 = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
+                    if (s1 == wsc) j = min(j, cc * 32 + lane);
                 }
+                j = __reduce_min_sync(PPG_FULL, j);
             } else {
-                warp_argmax(best, j);
+                int key = 0x7fffffff;
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const double s1 = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
+                    if (s1 > PPG_OPT_TOL) key = min(key, nbv[cc]);
+                }
+                const int wkey = __reduce_min_sync(PPG_FULL, key);
+                if (wkey == 0x7fffffff) { out.code = PPG_LP_OPTIMAL; return out; }
+                j = 0x7fffffff;
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc)
+                    if (nbv[cc] == wkey && kind[cc] != 0) j = min(j, cc * 32 + lane);
+                j = __reduce_min_sync(PPG_FULL, j);
             }
-            if (j == 0x7fffffff) { out.code = PPG_LP_OPTIMAL; return out; }
-            double aj = 0.0;
+            double aj = 0.0; int kj = 0, enter_var = 0;
 #pragma unroll
             for (int cc = 0; cc < CPL; ++cc) {
                 const double v = shfl_d(alpha[cc], j & 31);
-                if (cc == (j >> 5)) aj = v;
+                const int k2 = __shfl_sync(PPG_FULL, kind[cc], j & 31);
+                const int n2 = __shfl_sync(PPG_FULL, nbv[cc], j & 31);
+                if (cc == (j >> 5)) { aj = v; kj = k2; enter_var = n2; }
             }
-            const bool entering_free = sh.kind[j] == 1;
-            const int enter_var = sh.nbvar[j];
+            const bool entering_free = kj == 1;
             const double dir = (entering_free && aj > 0.0) ? -1.0 : 1.0;
-            // ratio test, Harris pass 1: largest admissible step with the rhs relaxed by PPG_HARRIS
+            // ---- ratio test inside the warp: min rhs/a, ties -> largest pivot (Bland: smallest basic id), then row
             double colv[RPT];
-            double tmax = CUDART_INF; int dummy = 0;
+            double lr = CUDART_INF, lp = 0.0; int lrow = 0x7fffffff, lb = 0x7fffffff;
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 colv[rr] = dir * reg_pick<DC>(T[rr], j);
                 if (rflag[rr] == 1 && colv[rr] > PPG_PIV_TOL) {
-                    const double rhs = fmax(T[rr][0], 0.0);
-                    tmax = fmin(tmax, (rhs + PPG_HARRIS) / colv[rr]);
+                    const double ratio = fmax(T[rr][0], 0.0) * (1.0 / colv[rr]);
+                    const int row = rr * GT + tid;
+                    const bool better = ratio < lr || (ratio == lr && (bland ? bvar[rr] < lb : colv[rr] > lp));
+                    if (better) { lr = ratio; lp = colv[rr]; lrow = row; lb = bvar[rr]; }
                 }
             });
-            group_argmin(sh, 0, warp, lane, tmax, dummy);
-            if (tmax == CUDART_INF) { out.code = PPG_LP_UNBOUNDED; out.beta = CUDART_INF; return out; }
-            // pass 2: among rows that block within tmax take the largest pivot (Bland: the smallest basic variable)
-            double bp = -1.0; int r = 0x7fffffff;
-            static_for<RPT>([&](auto RR) {
-                constexpr int rr = decltype(RR)::value;
-                if (rflag[rr] == 1 && colv[rr] > PPG_PIV_TOL) {
-                    const double rhs = fmax(T[rr][0], 0.0);
-                    if (rhs / colv[rr] <= tmax) {
-                        const int row = rr * GT + tid;
-                        const double key = bland ? -(double)bvar[rr] : colv[rr];
-                        if (key > bp || (key == bp && row < r)) { bp = key; r = row; }
-                    }
+            const double wr = warp_min_nonneg(lr);
+            int wrow = 0x7fffffff;
+            if (wr != CUDART_INF) {
+                const bool el = lr == wr;
+                if (bland) {
+                    const int wb = __reduce_min_sync(PPG_FULL, el ? lb : 0x7fffffff);
+                    wrow = __reduce_min_sync(PPG_FULL, (el && lb == wb) ? lrow : 0x7fffffff);
+                } else {
+                    const double wp = warp_max_nonneg(el ? lp : 0.0);
+                    wrow = __reduce_min_sync(PPG_FULL, (el && lp == wp) ? lrow : 0x7fffffff);
                 }
-            });
-            group_argmax(sh, 1, warp, lane, bp, r);
-            // the owner publishes the pivot row (pivot-column entry := 1), the effective pivot and the row's rhs
-            if (tid == r % GT) {
+            }
+            // ---- the warp's winner publishes its row; one barrier; every thread picks the global winner
+            double* Pw = &sh.P[buf][warp][0];
+            if (wrow == 0x7fffffff) {
+                if (lane == 0) sh.c_ratio[buf][warp] = CUDART_INF;
+            } else if (tid == wrow % GT) {
                 static_for<RPT>([&](auto RR) {
                     constexpr int rr = decltype(RR)::value;
-                    if (rr == r / GT) {
+                    if (rr == wrow / GT) {
 #pragma unroll
-                        for (int c = 0; c < DC; ++c) sh.P[c] = T[rr][c];
-                        sh.pinfo[0] = colv[rr];
-                        sh.pinfo[1] = T[rr][0];
-                        sh.nbvar[j] = bvar[rr];
-                        if (!entering_free) bvar[rr] = enter_var;
+                        for (int c = 0; c < DC; ++c) Pw[c] = T[rr][c];
+                        sh.c_piv[buf][warp] = colv[rr];
+                        sh.c_rhs[buf][warp] = T[rr][0];
+                        sh.c_bvar[buf][warp] = bvar[rr];
                     }
                 });
-                sh.P[j] = 1.0;
-                sh.kind[j] = 2;
+                Pw[j] = 1.0;
+                sh.c_ratio[buf][warp] = wr;
+                sh.c_row[buf][warp] = wrow;
             }
             gsync();
-            const double pj = sh.pinfo[0];
-            const double step = fmax(sh.pinfo[1], 0.0) / pj;
-            const double inv = 1.0 / pj;
+            double gr = sh.c_ratio[buf][0]; int gw = 0;
+            if constexpr (NW > 1) {
+                double gp = gr != CUDART_INF ? sh.c_piv[buf][0] : 0.0;
+                int gb = gr != CUDART_INF ? sh.c_bvar[buf][0] : 0x7fffffff;
+#pragma unroll
+                for (int w = 1; w < NW; ++w) {
+                    const double r2 = sh.c_ratio[buf][w];
+                    if (r2 == CUDART_INF) continue;
+                    const double p2 = sh.c_piv[buf][w];
+                    const int b2 = sh.c_bvar[buf][w];
+                    const bool better = r2 < gr || (r2 == gr && (bland ? b2 < gb : p2 > gp));  // row order == warp order
+                    if (better) { gr = r2; gp = p2; gb = b2; gw = w; }
+                }
+            }
+            if (gr == CUDART_INF) { out.code = PPG_LP_UNBOUNDED; out.beta = CUDART_INF; return out; }
+            const int r = sh.c_row[buf][gw];
+            const int leave_var = sh.c_bvar[buf][gw];
+            const double inv = 1.0 / sh.c_piv[buf][gw];
+            const double step = fmax(sh.c_rhs[buf][gw], 0.0) * inv;
+            const double* P = &sh.P[buf][gw][0];
             if (step <= PPG_DEGEN_STEP) { if (++degen > PPG_BLAND_AFTER) bland = true; } else degen = 0;
-            eliminate(sh, T, rflag, tid, r, j, inv, dir, !entering_free);
-            // objective row (replicated): alpha -= (dir*alpha_j*inv) * P', with alpha_j := 0 first
+            eliminate(P, T, rflag, colv, tid, r, j, inv, !entering_free);
+            // objective row and column bookkeeping (replicated): alpha -= (dir*alpha_j*inv) * P', alpha_j := 0 first
             {
                 const double f = dir * aj * inv;
 #pragma unroll
@@ -412,18 +447,22 @@ struct LpCore {
                     const int c = cc * 32 + lane;
                     if (c < DC) {
                         const double a0 = (c == j) ? 0.0 : alpha[cc];
-                        alpha[cc] = fma(-f, sh.P[c], a0);
+                        alpha[cc] = fma(-f, P[c], a0);
+                        if (c == j) { kind[cc] = 2; nbv[cc] = leave_var; }
                     }
                 }
             }
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
-                if (entering_free && rr * GT + tid == r) rflag[rr] = 0;
+                if (rr * GT + tid == r) {
+                    if (entering_free) rflag[rr] = 0; else bvar[rr] = enter_var;
+                }
                 if (rflag[rr] == 1 && T[rr][0] < 0.0 && T[rr][0] > -1e-9) T[rr][0] = 0.0;
             });
             out.pivots++; out.work += (long long)live * (ncol + 1);
             if (entering_free) live--;
-            gsync();
+            buf ^= 1;
+            if constexpr (NW == 1) __syncwarp();
         }
     }
 };
