@@ -11,6 +11,8 @@
 #include "lp_core.cuh"
 #include "launch.h"
 
+#include <cstdlib>
+
 namespace ppgpu {
 
 // resident CTAs per SM the register allocator is asked to make room for: the tableau needs 2*RPT*DC registers per
@@ -136,6 +138,13 @@ static cudaError_t launch_k2_t(const DevProgram& P, const uint64_t* masks, long 
         default: return cudaErrorInvalidValue;                                                         \
     }
 
+#define K2_DC_SWITCH_2x2()                                                                           \
+    switch (dc) {                                                                                      \
+        case 32: return launch_k2_t<2, 2, 32>(P, masks, n, status, queue, counters, sm_count, st);     \
+        case 40: return launch_k2_t<2, 2, 40>(P, masks, n, status, queue, counters, sm_count, st);     \
+        default: return cudaErrorInvalidValue;                                                         \
+    }
+
 int k2_pad_columns(int ncols_with_rhs) {
     const int opts[] = {8, 16, 24, 32, 40, 48, 64};
     for (int o : opts) if (ncols_with_rhs <= o) return o;
@@ -152,7 +161,13 @@ cudaError_t launch_k2(const DevProgram& P, const uint64_t* masks, long long n, u
         if (dc <= 24) { K2_DC_SWITCH_SMALL(1, 2) }
         K2_DC_SWITCH_LARGE(2, 1)
     }
-    if (P.R0 <= 128) { K2_DC_SWITCH(4, 1) }
+    if (P.R0 <= 128) {
+        // 65-128 rows: 2 warps x 2 rows per thread beats 4 warps x 1 row (measured 226 vs 250 ms on the 112 x 38
+        // tableau): the per-pivot bookkeeping is paid per warp, the rank-1 update per row.  PPGPU_K2_CFG=4x1 overrides.
+        const char* cfg = getenv("PPGPU_K2_CFG");
+        if (!(cfg && cfg[0] == '4') && dc <= 40 && dc >= 32) { K2_DC_SWITCH_2x2() }
+        K2_DC_SWITCH(4, 1)
+    }
     K2_DC_SWITCH(8, 1)
 }
 
