@@ -1,0 +1,161 @@
+"""GPU tests beyond the golden vectors: size-independent properties at the headline size, K6 against the reference's
+set arithmetic under arbitrary feasibility patterns, edge cases, slice/whole equivalence."""
+import os
+import sys
+
+import numpy
+import pytest
+
+from conftest import GOLDEN, ROOT
+from parity import masks_to_lists
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+
+def _engine(name):
+    from ppopt_b200 import engine
+    from ppopt_b200.mplp_program import load_presolved
+    prog = load_presolved(os.path.join(GOLDEN, name + '.npz'))
+    return engine, prog, engine.Engine(engine.program_arrays(prog))
+
+
+def _lex_sorted(lists):
+    return all(a < b for a, b in zip(lists, lists[1:]))
+
+
+@pytest.mark.parametrize('name', ['factory_mpqp', 'synthetic_30_6_40_s0', 'transport_mplp'])
+def test_k6_matches_reference_set_arithmetic_for_arbitrary_feasibility(name):
+    """next-level generation + superset pruning against CombinationTester/generate_children_sets
+    (solver_utils.py:29-55,154-166) when 'feasible' is an arbitrary pseudo-random predicate (W = 1 and W = 2 masks,
+    mpQP and mpLP cardinality filter)."""
+    import torch
+    from ppopt_b200.mp_solvers.solver_utils import CombinationTester, generate_children_sets
+    engine, prog, eng = _engine(name)
+    is_lp = type(prog).__name__ == 'MPLP_Program'
+    m, n, ne = prog.num_constraints(), prog.num_x(), len(prog.equality_indices)
+    rng = numpy.random.default_rng(5)
+    tester = CombinationTester()
+    to_check = generate_children_sets(prog.equality_indices, m, tester)
+    masks = eng.root_level()
+    for level in range(1, 4):
+        if is_lp:
+            to_check = [c for c in to_check if not (c[-1] >= len(c) + m - n)]
+        assert masks_to_lists(masks.cpu().numpy(), ne) == to_check, f'level {level}'
+        if len(to_check) > 3000:  # thin the level (keeps the reference-side python loops short)
+            keep_p = 3000.0 / len(to_check)
+        else:
+            keep_p = 0.8
+        feas = rng.random(len(to_check)) < keep_p
+        status = torch.from_numpy(numpy.where(feas, 3, 1).astype(numpy.uint8)).to(eng.tdev)
+        feasible = []
+        for c, ok in zip(to_check, feas):
+            if ok:
+                feasible.append(c)
+            else:
+                tester.add_combo(c)
+        nxt = []
+        for c in feasible:
+            nxt.extend(generate_children_sets(c, m, tester))
+        idx = eng.select(status, 2, 2)
+        assert idx.cpu().tolist() == numpy.nonzero(feas)[0].tolist()
+        masks = eng.children(masks, idx, level)
+        to_check = nxt
+        if not to_check:
+            assert masks.shape[0] == 0
+            break
+    eng.close()
+
+
+def test_headline_size_properties():
+    """synthetic 100x30x6, levels 1..4 (3.94e6 candidates): sortedness, cardinality, idempotence, agreement with the CPU
+    checker and with the reference-algorithm oracle on random samples, closure of the pruning rule."""
+    import torch
+    import ppopt_oracle as oracle
+    import twin_binding
+    engine, prog, eng = _engine('synthetic_30_6_40_s0')
+    path = os.path.join(GOLDEN, 'synthetic_30_6_40_s0.npz')
+    sol = engine.solve(prog, max_levels=4, engine=eng, collect_status=True)
+    sizes = [s['candidates'] for s in sol.level_stats]
+    assert sizes[:2] == [100, 4950] and sizes[2] == 158760 and sizes[3] == 3776565
+    tw = twin_binding.Twin.from_npz(path)
+    P = oracle.Program.from_npz(path)
+    rng = numpy.random.default_rng(11)
+    feas_prev = None
+    for lv, (masks, status) in enumerate(sol.level_status):
+        m64 = masks.view(numpy.uint64).reshape(len(masks), -1)
+        pc = numpy.unpackbits(m64.view(numpy.uint8), axis=1).sum(axis=1)
+        assert numpy.all(pc == lv + 1)
+        # lexicographic order of index lists == descending order of the bit-reversed key (checked on a sample of pairs)
+        pick = numpy.sort(rng.choice(len(masks) - 1, size=min(4000, len(masks) - 1), replace=False))
+        a = masks_to_lists(masks[pick], 0)
+        b = masks_to_lists(masks[pick + 1], 0)
+        assert all(x < y for x, y in zip(a, b)), f'level {lv + 1} not sorted'
+        # idempotence: re-evaluating the level reproduces the status bytes
+        again = eng.level_eval(torch.from_numpy(masks).to(eng.tdev), lv + 1).cpu().numpy()
+        assert numpy.array_equal(again & 7, status & 7)
+        # CPU checker on a sample (every decision bit), oracle (reference algorithm, HiGHS) on a smaller one
+        pick = rng.choice(len(masks), size=min(3000, len(masks)), replace=False)
+        assert numpy.array_equal(tw.eval(masks[pick]) & 11, status[pick] & 11), f'level {lv + 1} vs CPU checker'
+        for i in rng.choice(len(masks), size=40, replace=False):
+            aset = masks_to_lists(masks[i:i + 1], 0)[0]
+            assert oracle.evaluate_candidate(P, aset) & 11 == int(status[i]) & 11, (lv + 1, aset)
+        # pruning closure: every candidate's (k-1)-subsets are feasible members of the previous level
+        if feas_prev is not None:
+            for i in rng.choice(len(masks), size=300, replace=False):
+                aset = masks_to_lists(masks[i:i + 1], 0)[0]
+                for j in range(len(aset)):
+                    assert tuple(aset[:j] + aset[j + 1:]) in feas_prev
+        if lv < 3:
+            feas_prev = set(map(tuple, masks_to_lists(masks[(status & 2) != 0], 0)))
+    assert not any(sol.engine_counters[k] for k in ('numeric', 'border'))
+    eng.close()
+
+
+def test_slice_evaluation_equals_whole_level():
+    """the multi-GPU path evaluates [lo, hi) slices of a level: statuses must not depend on the slicing"""
+    import torch
+    engine, prog, eng = _engine('mpc_n5')
+    g = numpy.load(os.path.join(GOLDEN, 'mpc_n5.npz'))
+    cands = g['level3_candidates'].tolist()
+    masks = eng.masks_from_lists(cands)
+    whole = eng.level_eval(masks, 4).cpu().numpy()
+    parts = torch.zeros(len(cands), dtype=torch.uint8, device=eng.tdev)
+    cuts = [0, 1, 17, 500, 501, len(cands)]
+    for lo, hi in zip(cuts, cuts[1:]):
+        eng.level_eval(masks, 4, parts, 7, lo, hi)
+    assert numpy.array_equal(parts.cpu().numpy(), whole)
+    assert numpy.array_equal(whole & 3, g['level3_status'] & 3)
+    eng.close()
+
+
+def test_edge_cases():
+    import torch
+    engine, prog, eng = _engine('factory_mpqp')
+    # empty level
+    empty = eng.empty((0, eng.W), torch.int64)
+    assert eng.level_eval(empty, 1).shape[0] == 0
+    assert eng.select(torch.zeros(0, dtype=torch.uint8, device=eng.tdev), 2, 2).shape[0] == 0
+    assert eng.children(empty, eng.empty((0,), torch.int64), 1).shape[0] == 0
+    # the empty active set is full rank by definition (constraint_utilities.py:231-232) and feasible
+    st = eng.level_eval(torch.zeros((1, eng.W), dtype=torch.int64, device=eng.tdev), 0).cpu().numpy()
+    assert st[0] & 3 == 3
+    # more active rows than variables can never be full rank
+    st = eng.level_eval(eng.masks_from_lists([[0, 1, 2, 3, 4]]), 5, stages=1).cpu().numpy()
+    assert st[0] & 1 == 0
+    eng.close()
+    # reference test tests/other_tests/test_mpqp_utils.py:5-12 on the same fixture: [] and [0] feasible
+    from ppopt_b200.mp_solvers.mpqp_combinatorial import check_child_feasibility
+    from ppopt_b200.mp_solvers.solver_utils import CombinationTester
+    t = CombinationTester()
+    out = check_child_feasibility(prog, [[], [0], [2, 3], [0, 1, 2, 3, 4]], t)
+    assert out == [[], [0], [2, 3]] and t.combos == {(0, 1, 2, 3, 4)}
+
+
+def test_status_bytes_stay_on_device_and_counters_move():
+    engine, prog, eng = _engine('mpc_n3')
+    sol = engine.solve(prog, engine=eng)
+    c = sol.engine_counters
+    assert c['k2_lps'] > 0 and c['k2_pivots'] > c['k2_lps'] and c['k4_lps'] > 0 and sol.gpu_launches > 10
+    assert len(sol.critical_regions) == 7
+    eng.close()
