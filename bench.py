@@ -6,7 +6,7 @@
 
 Workload (config.workload): BASELINE.json configs[4], the synthetic dense mpQP with 100 constraints / 30 variables /
 6 parameters = generate_mpqp(30, 6, 40, seed=0) after the reference's presolve (tests/golden/synthetic_30_6_40_s0.npz),
-combinatorial levels 1..L (default L = 4: 3,940,375 candidate active sets; the reference cannot finish more than
+combinatorial levels 1..L (default L = 5: 78,385,935 candidate active sets; L = 4: 3,940,375; the reference cannot finish more than
 L = 3 in any reasonable time).  A "step" is one full pass of the level loop over that program.
 
   value   device-resident throughput: program constants already in HBM, every kernel of the path runs (K1 rank, K2
@@ -300,10 +300,10 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--levels', type=int, default=4)
+    ap.add_argument('--levels', type=int, default=5)
     ap.add_argument('--workload', default='synthetic_30_6_40_s0', choices=list(WORKLOADS))
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -298,6 +298,15 @@ int kkt_cheb_gram(Twin& tw, const std::vector<int>& act, double* rad) {
             L[(size_t)i * (t + 1) + col] = s / S[(size_t)i * k + i];
         }
     }
+    for (int j = 0; j < k; ++j) {  // multiplier-sign test over the bounding box of Theta (necessary condition)
+        double ub = L[(size_t)j * (t + 1)], mx = 0.0, mag = std::fabs(ub);
+        for (int c = 0; c < t; ++c) {
+            const double a = L[(size_t)j * (t + 1) + 1 + c];
+            mx = std::fmax(mx, std::fabs(a));
+            if (a != 0.0) { const double term = std::fmax(a * P.th_lo[c], a * P.th_hi[c]); ub += term; mag += std::fabs(term); }
+        }
+        if (mx > PPG_ZERO_ROW && ub < -1e-9 * std::fmax(1.0, mag)) { if (rad) *rad = -INFINITY; return 0; }
+    }
     std::vector<double> rows((size_t)P.R0 * (t + 1));
     std::vector<int> pos(mi, -1);
     for (int a = 0; a < k; ++a) pos[act[a]] = a;

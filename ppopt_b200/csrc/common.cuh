@@ -17,6 +17,7 @@ struct DevProgram {
     const double* T0;   // R0 x dc0     base feasibility tableau [rhs | v | theta | s] (K2)
     const double* G;    // mi x mi      Gram  At Qr^-1 At'  (K3)
     const double* V;    // mi x (t+1)   [const | theta] right-hand sides of the Schur system (K3)
+    const double* th_lo; const double* th_hi;  // t  outer bounding box of Theta (K3 multiplier-sign test)
     const double* A; const double* b; const double* F;      // originals (K5)
     const double* A_t; const double* b_t;
     const double* Q; const double* c; const double* H;

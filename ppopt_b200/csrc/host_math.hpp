@@ -32,6 +32,9 @@ struct ReducedProgram {
     vec T0;
     // K3: Gram G (mi x mi) and V (mi x (t+1)) with layout [const | theta coefficients]
     vec G, V;
+    // outer bounding box of Theta from the single-variable rows of A_t theta <= b_t (+-inf where there is none);
+    // used by K3 as a cheap NECESSARY test: lambda_j(theta) must be able to reach >= 0 somewhere in the box
+    vec th_lo, th_hi;
     // originals (row major), kept for region emission
     vec A, b, F, At_theta, bt, Q, c, H;
     std::string error;
@@ -164,6 +167,17 @@ inline bool reduce_program(int n, int t, int m, int q, int ne, int is_qp, const 
         r[0] = b_t[i];
         for (int j = 0; j < t; ++j) r[1 + np + j] = A_t[(size_t)i * t + j];
         r[1 + np + t] = 1.0;
+    }
+    P.th_lo.assign(t, -INFINITY);
+    P.th_hi.assign(t, INFINITY);
+    for (int i = 0; i < q; ++i) {
+        int nz = 0, col = -1;
+        for (int j = 0; j < t; ++j)
+            if (A_t[(size_t)i * t + j] != 0.0) { ++nz; col = j; }
+        if (nz == 1) {
+            const double a = A_t[(size_t)i * t + col], v = b_t[i] / a;
+            if (a > 0) P.th_hi[col] = std::fmin(P.th_hi[col], v); else P.th_lo[col] = std::fmax(P.th_lo[col], v);
+        }
     }
     // ---- K3 Gram data (only when the reduced Hessian is symmetric positive definite)
     P.use_gram = 0;

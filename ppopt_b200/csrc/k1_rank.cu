@@ -117,11 +117,115 @@ static cudaError_t launch_k1_t(const DevProgram& P, const uint64_t* masks, long 
     return cudaGetLastError();
 }
 
+
+// Small active sets (k' <= 16): GS = 4/8/16 lanes per candidate, 32/GS candidates per warp.  Every lane of the warp
+// runs the same k' Householder steps (uniform shuffles); a group that has already decided just stops updating.
+template <int NP, int GS>
+__global__ void __launch_bounds__(128)
+k1_rank_group_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k, uint8_t* __restrict__ status,
+                     unsigned long long* __restrict__ counters) {
+    constexpr int CPW = 32 / GS;
+    const int lane = threadIdx.x & 31, gl = lane % GS, gid = lane / GS, gbase = gid * GS;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int W = P.W, np = P.np;
+    unsigned long long n_border = 0;
+    for (long long base = warp0 * CPW; base < n; base += nwarps * CPW) {
+        const long long idx = base + gid;
+        const bool valid = idx < n;
+        const uint64_t* mk = masks + (valid ? idx : 0) * W;
+        double col[NP];
+        bool done = !(valid && gl < k);
+        {
+            const int a = done ? -1 : mask_nth(mk, W, gl);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) col[i] = (a >= 0 && i < np) ? __ldg(P.At + (size_t)a * np + i) : 0.0;
+        }
+        double first = 0.0, minratio = 1.0;
+        bool full = true, alive = valid;
+        for (int s = 0; s < k; ++s) {
+            double best = -1.0; int pj = gl;
+            if (!done) {
+                double nn = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) if (i >= s) nn = fma(col[i], col[i], nn);
+                best = nn;
+            }
+#pragma unroll
+            for (int o = GS / 2; o > 0; o >>= 1) {
+                const double ov = shfl_xor_d(best, o);
+                const int oj = __shfl_xor_sync(PPG_FULL, pj, o);
+                if (ov > best || (ov == best && oj < pj)) { best = ov; pj = oj; }
+            }
+            const double rss = sqrt(fmax(best, 0.0));
+            if (s == 0) first = rss;
+            if (alive) {
+                if (first == 0.0) { full = false; alive = false; minratio = 0.0; }
+                else {
+                    const double ratio = rss / first;
+                    minratio = fmin(minratio, ratio);
+                    if (ratio <= PPG_RANK_TOL) { full = false; alive = false; }
+                }
+            }
+            double v[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) v[i] = (i >= s) ? shfl_d(col[i], gbase + pj) : 0.0;
+            double vs = 0.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) if (i == s) vs = v[i];
+            const double alpha = vs >= 0.0 ? -rss : rss;
+            double vtv = 0.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                if (i == s) v[i] -= alpha;
+                vtv = fma(v[i], v[i], vtv);
+            }
+            if (gl == pj) done = true;
+            if (alive && !done && vtv > 0.0) {
+                double d = 0.0;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) d = fma(v[i], col[i], d);
+                d = 2.0 * d / vtv;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) col[i] = fma(-d, v[i], col[i]);
+            }
+        }
+        if (valid && gl == 0) {
+            uint8_t st = full ? PPG_ST_RANK : 0;
+            if (minratio > PPG_RANK_BORDER_LO && minratio < PPG_RANK_BORDER_HI) { st |= PPG_ST_BORDER; n_border++; }
+            status[idx] = st;
+        }
+    }
+    if (n_border) atomicAdd(&counters[CNT_BORDER], n_border);
+}
+
+template <int NP, int GS>
+static cudaError_t launch_k1_g(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                               unsigned long long* counters, int sm_count, cudaStream_t st) {
+    const int threads = 128;
+    const long long per_block = (threads / 32) * (32 / GS);
+    long long blocks = (n + per_block - 1) / per_block;
+    const long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k1_rank_group_kernel<NP, GS><<<(unsigned)blocks, threads, 0, st>>>(P, masks, n, k_act, status, counters);
+    return cudaGetLastError();
+}
+
+template <int NP>
+static cudaError_t launch_k1_np(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                                unsigned long long* counters, int sm_count, cudaStream_t st) {
+    if (k_act >= 1 && k_act <= 4) return launch_k1_g<NP, 4>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (k_act >= 1 && k_act <= 8) return launch_k1_g<NP, 8>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (k_act >= 1 && k_act <= 16) return launch_k1_g<NP, 16>(P, masks, n, k_act, status, counters, sm_count, st);
+    return launch_k1_t<NP, 1>(P, masks, n, k_act, status, counters, sm_count, st);
+}
+
 cudaError_t launch_k1(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                       unsigned long long* counters, int sm_count, cudaStream_t st) {
-    if (P.np <= 8) return launch_k1_t<8, 1>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (P.np <= 16) return launch_k1_t<16, 1>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (P.np <= 32) return launch_k1_t<32, 1>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (P.np <= 8) return launch_k1_np<8>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (P.np <= 16) return launch_k1_np<16>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (P.np <= 32) return launch_k1_np<32>(P, masks, n, k_act, status, counters, sm_count, st);
     if (P.np <= 64) return launch_k1_t<64, 2>(P, masks, n, k_act, status, counters, sm_count, st);
     return cudaErrorInvalidValue;
 }

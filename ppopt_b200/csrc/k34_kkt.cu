@@ -90,6 +90,22 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
                 }
             }
             __syncwarp();
+            // cheap NECESSARY condition before the expensive part: every nonzero multiplier row must be able to reach
+            // lambda_j(theta) > 0 somewhere in the bounding box of Theta (else the theta-polytope is empty)
+            bool reject = false;
+            for (int j = lane; j < k; j += 32) {
+                double ub = Lam[j * t1], mx = 0.0, mag = fabs(Lam[j * t1]);
+                for (int c = 0; c < t; ++c) {
+                    const double a = Lam[j * t1 + 1 + c];
+                    const double lo = __ldg(P.th_lo + c), hi = __ldg(P.th_hi + c);
+                    mx = fmax(mx, fabs(a));
+                    if (a != 0.0) { const double term = fmax(a * lo, a * hi); ub += term; mag += fabs(term); }
+                }
+                if (mx > PPG_ZERO_ROW && ub < -1e-9 * fmax(1.0, mag)) reject = true;
+            }
+            if (__any_sync(PPG_FULL, reject)) {
+                continue;  // not optimal: status keeps PPG_ST_FEAS only
+            }
             // region rows straight into the tableau registers: T[.][0] = f, T[.][1..t] = a, T[.][t+1] = 1 (the s column)
             double T[RPT][DC];
             int rflag[RPT];
