@@ -115,6 +115,7 @@ struct LpShared {
     double P[2][NW][DC];    // candidate pivot rows, one per warp, ping-pong over iterations (pivot-column entry := 1)
     double c_ratio[2][NW];  // per-warp ratio-test winner: step length, effective pivot, rhs, row, basic-variable id
     double c_piv[2][NW];
+    double c_inv[2][NW];
     double c_rhs[2][NW];
     int c_row[2][NW];
     int c_bvar[2][NW];
@@ -323,46 +324,58 @@ struct LpCore {
             gsync();
         }
         // ---------------- Phase C: primal simplex on the objective "s", ONE barrier per pivot ----------------
+        // Latency-trimmed (profiles/r01: the pivot was a ~800-cycle dependent chain with 2 warps per scheduler):
+        //  * Dantzig pricing only needs an approximately largest score -> one 32-bit redux on float keys + ballots;
+        //    the optimality test itself stays exact (fp64 compare per lane);
+        //  * the ratio test first filters rows with float keys (one redux); the true minimiser is always inside the
+        //    filter band, and when the band holds a single row (the common case) no fp64 reduction runs at all;
+        //  * the winner publishes 1/pivot, nobody divides after the barrier; beta is kept by every lane.
         int degen = 0; bool bland = false;
         const int cap = 50 * (nrows + ncol) + 200;
         int buf = 0;
+        double beta = shfl_d(alpha[0], 0);
         for (int it = 0;; ++it) {
-            const double beta = shfl_d(alpha[0], 0);
             out.beta = beta;
             if (strict ? (beta > thr) : (beta >= thr)) { out.code = PPG_LP_EARLY; return out; }
             if (it > cap) { out.code = PPG_LP_ITERLIM; return out; }
             // ---- pricing: lanes over columns, identical in every warp (no communication between warps)
             int j;
-            if (!bland) {
-                double sc = 0.0;
+            {
+                double sc[CPL];
+                bool el = false;
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) {
-                    const double s1 = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
-                    sc = fmax(sc, s1);
+                    sc[cc] = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
+                    el = el || sc[cc] > PPG_OPT_TOL;
                 }
-                const double wsc = warp_max_nonneg(fmax(sc, 0.0));
-                if (!(wsc > PPG_OPT_TOL)) { out.code = PPG_LP_OPTIMAL; return out; }
-                j = 0x7fffffff;
+                if (!__any_sync(PPG_FULL, el)) { out.code = PPG_LP_OPTIMAL; return out; }
+                if (!bland) {
+                    unsigned key[CPL], lk = 0u;
 #pragma unroll
-                for (int cc = 0; cc < CPL; ++cc) {
-                    const double s1 = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
-                    if (s1 == wsc) j = min(j, cc * 32 + lane);
+                    for (int cc = 0; cc < CPL; ++cc) {
+                        key[cc] = sc[cc] > PPG_OPT_TOL ? __float_as_uint(fmaxf((float)sc[cc], 1e-37f)) : 0u;
+                        lk = max(lk, key[cc]);
+                    }
+                    const unsigned wk = __reduce_max_sync(PPG_FULL, lk);
+                    j = 0x7fffffff;
+#pragma unroll
+                    for (int cc = CPL - 1; cc >= 0; --cc) {
+                        const unsigned m = __ballot_sync(PPG_FULL, key[cc] == wk);
+                        if (m) j = cc * 32 + __ffs((int)m) - 1;
+                    }
+                } else {
+                    int key = 0x7fffffff;
+#pragma unroll
+                    for (int cc = 0; cc < CPL; ++cc)
+                        if (sc[cc] > PPG_OPT_TOL) key = min(key, nbv[cc]);
+                    const int wkey = __reduce_min_sync(PPG_FULL, key);
+                    j = 0x7fffffff;
+#pragma unroll
+                    for (int cc = CPL - 1; cc >= 0; --cc) {
+                        const unsigned m = __ballot_sync(PPG_FULL, nbv[cc] == wkey && kind[cc] != 0);
+                        if (m) j = cc * 32 + __ffs((int)m) - 1;
+                    }
                 }
-                j = __reduce_min_sync(PPG_FULL, j);
-            } else {
-                int key = 0x7fffffff;
-#pragma unroll
-                for (int cc = 0; cc < CPL; ++cc) {
-                    const double s1 = kind[cc] == 1 ? fabs(alpha[cc]) : (kind[cc] == 2 ? -alpha[cc] : 0.0);
-                    if (s1 > PPG_OPT_TOL) key = min(key, nbv[cc]);
-                }
-                const int wkey = __reduce_min_sync(PPG_FULL, key);
-                if (wkey == 0x7fffffff) { out.code = PPG_LP_OPTIMAL; return out; }
-                j = 0x7fffffff;
-#pragma unroll
-                for (int cc = 0; cc < CPL; ++cc)
-                    if (nbv[cc] == wkey && kind[cc] != 0) j = min(j, cc * 32 + lane);
-                j = __reduce_min_sync(PPG_FULL, j);
             }
             double aj = 0.0; int kj = 0, enter_var = 0;
 #pragma unroll
@@ -376,30 +389,52 @@ struct LpCore {
             const double dir = (entering_free && aj > 0.0) ? -1.0 : 1.0;
             // ---- ratio test inside the warp: min rhs/a, ties -> largest pivot (Bland: smallest basic id), then row
             double colv[RPT];
-            double lr = CUDART_INF, lp = 0.0; int lrow = 0x7fffffff, lb = 0x7fffffff;
+            float kf[RPT];
+            float lkf = CUDART_INF_F;
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 colv[rr] = dir * reg_pick<DC>(T[rr], j);
-                if (rflag[rr] == 1 && colv[rr] > PPG_PIV_TOL) {
-                    const double ratio = fmax(T[rr][0], 0.0) * (1.0 / colv[rr]);
-                    const int row = rr * GT + tid;
-                    const bool better = ratio < lr || (ratio == lr && (bland ? bvar[rr] < lb : colv[rr] > lp));
-                    if (better) { lr = ratio; lp = colv[rr]; lrow = row; lb = bvar[rr]; }
-                }
+                const bool ok = rflag[rr] == 1 && colv[rr] > PPG_PIV_TOL;
+                kf[rr] = ok ? __fdividef((float)fmax(T[rr][0], 0.0), (float)colv[rr]) : CUDART_INF_F;
+                lkf = fminf(lkf, kf[rr]);
             });
-            const double wr = warp_min_nonneg(lr);
+            const float wkf = __uint_as_float(__reduce_min_sync(PPG_FULL, __float_as_uint(lkf)));
             int wrow = 0x7fffffff;
-            if (wr != CUDART_INF) {
-                const bool el = lr == wr;
-                if (bland) {
-                    const int wb = __reduce_min_sync(PPG_FULL, el ? lb : 0x7fffffff);
-                    wrow = __reduce_min_sync(PPG_FULL, (el && lb == wb) ? lrow : 0x7fffffff);
+            if (wkf != CUDART_INF_F) {
+                const float band = wkf * 1.00002f + 1e-30f;  // fp32 keys carry <= 4e-7 relative error: the true minimiser is inside
+                int ncl = 0, crow = 0x7fffffff;
+                static_for<RPT>([&](auto RR) {
+                    constexpr int rr = decltype(RR)::value;
+                    if (kf[rr] <= band) { ++ncl; crow = min(crow, rr * GT + tid); }
+                });
+                const unsigned m = __ballot_sync(PPG_FULL, ncl > 0);
+                const unsigned m2 = __ballot_sync(PPG_FULL, ncl > 1);
+                if ((m & (m - 1)) == 0u && m2 == 0u) {
+                    wrow = __shfl_sync(PPG_FULL, crow, __ffs((int)m) - 1);
                 } else {
-                    const double wp = warp_max_nonneg(el ? lp : 0.0);
-                    wrow = __reduce_min_sync(PPG_FULL, (el && lp == wp) ? lrow : 0x7fffffff);
+                    // several rows inside the band (degenerate vertex or a genuine near-tie): exact fp64 comparison
+                    double lr = CUDART_INF, lp = 0.0; int lrow = 0x7fffffff, lb = 0x7fffffff;
+                    static_for<RPT>([&](auto RR) {
+                        constexpr int rr = decltype(RR)::value;
+                        if (kf[rr] <= band) {
+                            const double ratio = fmax(T[rr][0], 0.0) * (1.0 / colv[rr]);
+                            const int row = rr * GT + tid;
+                            const bool better = ratio < lr || (ratio == lr && (bland ? bvar[rr] < lb : colv[rr] > lp));
+                            if (better) { lr = ratio; lp = colv[rr]; lrow = row; lb = bvar[rr]; }
+                        }
+                    });
+                    const double wr = warp_min_nonneg(lr);
+                    const bool el = lr == wr;
+                    if (bland) {
+                        const int wb = __reduce_min_sync(PPG_FULL, el ? lb : 0x7fffffff);
+                        wrow = __reduce_min_sync(PPG_FULL, (el && lb == wb) ? lrow : 0x7fffffff);
+                    } else {
+                        const double wp = warp_max_nonneg(el ? lp : 0.0);
+                        wrow = __reduce_min_sync(PPG_FULL, (el && lp == wp) ? lrow : 0x7fffffff);
+                    }
                 }
             }
-            // ---- the warp's winner publishes its row; one barrier; every thread picks the global winner
+            // ---- the warp's winner publishes its row (+ exact ratio, 1/pivot); one barrier; everyone picks the global winner
             double* Pw = &sh.P[buf][warp][0];
             if (wrow == 0x7fffffff) {
                 if (lane == 0) sh.c_ratio[buf][warp] = CUDART_INF;
@@ -409,13 +444,14 @@ struct LpCore {
                     if (rr == wrow / GT) {
 #pragma unroll
                         for (int c = 0; c < DC; ++c) Pw[c] = T[rr][c];
+                        const double ivp = 1.0 / colv[rr];
                         sh.c_piv[buf][warp] = colv[rr];
-                        sh.c_rhs[buf][warp] = T[rr][0];
+                        sh.c_inv[buf][warp] = ivp;
+                        sh.c_ratio[buf][warp] = fmax(T[rr][0], 0.0) * ivp;
                         sh.c_bvar[buf][warp] = bvar[rr];
+                        Pw[j] = dir * colv[rr] + 1.0;
                     }
                 });
-                Pw[j] = dir * sh.c_piv[buf][warp] + 1.0;
-                sh.c_ratio[buf][warp] = wr;
                 sh.c_row[buf][warp] = wrow;
             }
             gsync();
@@ -436,14 +472,13 @@ struct LpCore {
             if (gr == CUDART_INF) { out.code = PPG_LP_UNBOUNDED; out.beta = CUDART_INF; return out; }
             const int r = sh.c_row[buf][gw];
             const int leave_var = sh.c_bvar[buf][gw];
-            const double inv = 1.0 / sh.c_piv[buf][gw];
-            const double step = fmax(sh.c_rhs[buf][gw], 0.0) * inv;
+            const double inv = sh.c_inv[buf][gw];
             const double* P = &sh.P[buf][gw][0];
-            if (step <= PPG_DEGEN_STEP) { if (++degen > PPG_BLAND_AFTER) bland = true; } else degen = 0;
-            eliminate(P, T, rflag, colv, tid, r, j, inv, !entering_free);
+            if (gr <= PPG_DEGEN_STEP) { if (++degen > PPG_BLAND_AFTER) bland = true; } else degen = 0;
             // objective row and column bookkeeping (replicated): alpha -= (alpha_j / pivot) * P'
             {
                 const double f = dir * aj * inv;
+                beta = fma(-f, P[0], beta);
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) {
                     const int c = cc * 32 + lane;
@@ -453,6 +488,7 @@ struct LpCore {
                     }
                 }
             }
+            eliminate(P, T, rflag, colv, tid, r, j, inv, !entering_free);
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 if (rr * GT + tid == r) {
