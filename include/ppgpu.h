@@ -69,7 +69,8 @@ int ppgpu_root_level(ppgpu_program* prog, uint64_t* d_masks, int64_t* h_count, p
 /* check_child_feasibility + check_optimality for n candidates of cardinality n_eq + k_act:
  * K1 rank screen (is_full_rank, constraint_utilities.py:222-236), K2 feasibility LP (mplp_program.py:411-444),
  * K3/K4 optimality + full-dimension screen (mpqp_program.py:203-322, mpqp_utils.py:323-344).
- * Writes one status byte per candidate (PPG_ST_* bits of csrc/tolerances.h).  stages: bit0 K1, bit1 K2, bit2 K3/K4. */
+ * Writes one status byte per candidate (PPG_ST_* bits of csrc/tolerances.h).  stages: bit0 K1, bit1 K2 (preceded by the
+ * K2a relaxation certificates unless bit3 is set), bit2 K3/K4. */
 int ppgpu_level_eval(ppgpu_program* prog, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
                      int32_t stages, ppgpu_stream stream);
 
@@ -106,7 +107,7 @@ int64_t ppgpu_launch_count(const ppgpu_program* prog);
 
 /* Optional per-kernel-family timing with CUDA events recorded on the launch stream (used by bench.py for the
  * roofline line).  Families: 0 K1 rank, 1 K2 feasibility LP, 2 K3/K4 screen, 3 K5 emission, 4 K6 count, 5 K6 write,
- * 6 ordered compaction.  h_ms / h_launches hold PPGPU_NUM_FAMILIES entries. */
+ * 6 ordered compaction, 7 K2a relaxation certificates.  h_ms / h_launches hold PPGPU_NUM_FAMILIES entries. */
 #define PPGPU_NUM_FAMILIES 8
 int ppgpu_profile_enable(ppgpu_program* prog, int32_t on);
 int ppgpu_profile_read(ppgpu_program* prog, double* h_ms, int64_t* h_launches, int32_t reset);

@@ -15,6 +15,7 @@ struct DevProgram {
     int dc0;  // row stride of T0 = nfree + 2
     const double* At;   // mi x np      reduced inequality rows (K1)
     const double* T0;   // R0 x dc0     base feasibility tableau [rhs | v | theta | s] (K2)
+    const double* Gam;  // R0 x R0      Gram of the feasibility rows (K2a relaxation certificates)
     const double* G;    // mi x mi      Gram  At Qr^-1 At'  (K3)
     const double* V;    // mi x (t+1)   [const | theta] right-hand sides of the Schur system (K3)
     const double* th_lo; const double* th_hi;  // t  outer bounding box of Theta (K3 multiplier-sign test)
@@ -30,6 +31,7 @@ enum Counter {
     CNT_K4_LPS, CNT_K4_PIVOTS, CNT_K4_WORK,
     CNT_K5_LPS, CNT_K5_PIVOTS, CNT_K5_WORK,
     CNT_NUMERIC, CNT_BORDER, CNT_K6_LOOKUPS,
+    CNT_K2A_TRIED, CNT_K2A_CERTIFIED, CNT_K2A_STEPS,
     CNT_COUNT = 16
 };
 

@@ -30,6 +30,8 @@ struct ReducedProgram {
     vec At;
     // K2: base tableau rows (R0 x (nfree + 2)), column layout [rhs | v(np) | theta(t) | s]
     vec T0;
+    // K2a: Gram of the feasibility rows  Gam = Gf Gf' (R0 x R0), Gf = T0[:, 1..nfree]
+    vec Gam;
     // K3: Gram G (mi x mi) and V (mi x (t+1)) with layout [const | theta coefficients]
     vec G, V;
     // outer bounding box of Theta from the single-variable rows of A_t theta <= b_t (+-inf where there is none);
@@ -168,6 +170,13 @@ inline bool reduce_program(int n, int t, int m, int q, int ne, int is_qp, const 
         for (int j = 0; j < t; ++j) r[1 + np + j] = A_t[(size_t)i * t + j];
         r[1 + np + t] = 1.0;
     }
+    P.Gam.assign((size_t)P.R0 * P.R0, 0.0);
+    for (int i = 0; i < P.R0; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = 0.0;
+            for (int c = 0; c < P.nfree; ++c) s += P.T0[(size_t)i * dc + 1 + c] * P.T0[(size_t)j * dc + 1 + c];
+            P.Gam[(size_t)i * P.R0 + j] = P.Gam[(size_t)j * P.R0 + i] = s;
+        }
     P.th_lo.assign(t, -INFINITY);
     P.th_hi.assign(t, INFINITY);
     for (int i = 0; i < q; ++i) {

@@ -50,7 +50,7 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
         }
         if (idx >= n) break;
         const uint8_t st = status[idx];
-        if (!(st & PPG_ST_RANK)) continue;
+        if (!(st & PPG_ST_RANK) || (st & PPG_ST_FEAS)) continue;  // rank deficient, or already certified by K2a
         const uint64_t* mk = masks + idx * W;
         double T[RPT][DC];
         int rflag[RPT];
