@@ -166,8 +166,8 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
         // feasibility certificates first (cheap); the simplex only sees what is left
         ProfScope ps(p, st, 7);
         static const int iters = getenv("PPGPU_K2A_ITERS") ? atoi(getenv("PPGPU_K2A_ITERS")) : 96;
-        if (iters > 0) {
-            e = launch_k2a(p->dev, d_masks, n, k_act < 0 ? 0 : k_act, d_status, next_queue(p, st), p->d_counters, iters,
+        if (iters > 0 && k_act >= 0) {
+            e = launch_k2a(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, iters,
                            p->sm_count, st);
             if (e != cudaSuccess) return fail("K2a relaxation", e);
             p->launches++;
