@@ -20,6 +20,9 @@
 
 namespace ppgpu {
 
+__device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }  // no NaN fix-up (fmax costs ~10 SASS)
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 constexpr double K2A_OMEGA = 1.35;  // scanned 1.2 .. 1.8 on the 100x30x6 program: fewest steps (32 vs 39 at 1.5)
 
 template <int RPL>
@@ -243,13 +246,14 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
     extern __shared__ double dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R0 = P.R0, nf = P.nfree, dc0 = P.dc0, W = P.W, k = k_act;
-    // per-warp scratch: Sinv (KC x KC), ga (KC), cs (R0), zs (nf), act (KC ints)
-    const size_t per_warp = (size_t)KC * KC + KC + (size_t)R0 + (size_t)nf + (size_t)(KC / 2 + 1);
+    // per-warp scratch: Sinv (KC x KC), ga (KC), cs (R0), zs (nf), act (KC ints), touched rows (R0 ints)
+    const size_t per_warp = (size_t)KC * KC + KC + (size_t)R0 + (size_t)nf + (size_t)(KC / 2 + 1) + (size_t)(R0 / 2 + 1);
     double* Sinv = dyn_smem + per_warp * warp;
     double* ga = Sinv + KC * KC;
     double* cs = ga + KC;
     double* zs = cs + R0;
     int* act = reinterpret_cast<int*>(zs + nf);
+    int* touched = act + 2 * (KC / 2 + 1);
     const double* __restrict__ Gam = P.Gam;
     const double* __restrict__ T0 = P.T0;
     unsigned long long n_try = 0, n_ok = 0, n_it = 0;
@@ -317,20 +321,30 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
             __syncwarp();
         }
         if (!__all_sync(PPG_FULL, pd)) continue;
-        // ---- per-lane constants: rows of Gam[A,:] folded with Sinv, start residuals, start coefficients
+        // ---- per-lane constants: rows of Gam[A,:] folded with Sinv, start residuals, start coefficients.
+        // Addressing is hoisted out of the step loop (v1 of this kernel spent 2/3 of its instructions on 64-bit index
+        // arithmetic and bounds predicates): row pointers of the active rows, clamped row index per lane slot, and
+        // padded active slots that point at a valid row but carry M == 0.
         double M[RPL][KC], v[RPL];
-        bool isA[RPL];
-        int actr[KC];
+        bool isA[RPL], use[RPL];
+        const double* growA[KC];
 #pragma unroll
-        for (int a = 0; a < KC; ++a) actr[a] = (a < k) ? act[a] : 0;
+        for (int a = 0; a < KC; ++a) growA[a] = Gam + (size_t)act[a < k ? a : 0] * R0;
+        int rcl[RPL];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) rcl[rr] = min(rr * 32 + lane, R0 - 1);
         double cA = 0.0;  // coefficient of active row `lane` (lanes < k); inequality coefficients live in cs[]
+        int ntouched = 0; // distinct rows stepped on so far (their ids are in touched[])
+        double srow[KC];  // row `lane` of Sinv (lanes < KC)
+#pragma unroll
+        for (int b2 = 0; b2 < KC; ++b2) srow[b2] = Sinv[(lane < KC ? lane : 0) * KC + b2];
         {
             double w0[KC];
 #pragma unroll
             for (int a = 0; a < KC; ++a) {
                 double s2 = 0.0;
 #pragma unroll
-                for (int b = 0; b < KC; ++b) s2 = fma(Sinv[a * KC + b], (b < k) ? __ldg(T0 + (size_t)actr[b] * dc0) : 0.0, s2);
+                for (int b = 0; b < KC; ++b) s2 = fma(Sinv[a * KC + b], (b < k) ? __ldg(T0 + (size_t)act[b] * dc0) : 0.0, s2);
                 w0[a] = (a < k) ? s2 : 0.0;
                 if (a == lane) cA = w0[a];
             }
@@ -339,18 +353,19 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                 const int r = rr * 32 + lane;
                 double gA[KC];
 #pragma unroll
-                for (int a = 0; a < KC; ++a) gA[a] = (a < k && r < R0) ? __ldg(Gam + (size_t)actr[a] * R0 + r) : 0.0;
-                double s2 = (r < R0) ? -__ldg(T0 + (size_t)r * dc0) : 0.0;
+                for (int a = 0; a < KC; ++a) gA[a] = (a < k) ? __ldg(growA[a] + rcl[rr]) : 0.0;
+                double s2 = -__ldg(T0 + (size_t)rcl[rr] * dc0);
 #pragma unroll
                 for (int a = 0; a < KC; ++a) {
                     double m2 = 0.0;
 #pragma unroll
                     for (int b = 0; b < KC; ++b) m2 = fma(gA[b], Sinv[b * KC + a], m2);
-                    M[rr][a] = m2;
+                    M[rr][a] = (a < k) ? m2 : 0.0;
                     s2 = fma(gA[a], w0[a], s2);
                 }
                 v[rr] = s2;
                 isA[rr] = r < P.mi && mask_test(mk, r);
+                use[rr] = r < R0 && !isA[rr];
                 if (r < R0) cs[r] = 0.0;
             }
         }
@@ -360,8 +375,7 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
         for (int it = 0; it < max_iter; ++it) {
             double lv = 0.0;
 #pragma unroll
-            for (int rr = 0; rr < RPL; ++rr)
-                if (!isA[rr] && rr * 32 + lane < R0) lv = fmax(lv, v[rr]);
+            for (int rr = 0; rr < RPL; ++rr) lv = dmax2(lv, use[rr] ? v[rr] : 0.0);
             const double wmax = warp_max_nonneg(lv);
             if (wmax <= PPG_FEAS_TOL) {
                 // ---- exact verification: materialise z from the coefficients, recompute every near-binding row
@@ -373,9 +387,10 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                     const int c = cc * 32 + lane;
                     if (c < nf) {
                         double s2 = 0.0;
-                        for (int r = 0; r < R0; ++r) {
-                            const double cr = cs[r];
-                            if (cr != 0.0) s2 = fma(cr, __ldg(T0 + (size_t)r * dc0 + 1 + c), s2);
+                        for (int a2 = 0; a2 < k; ++a2) s2 = fma(cs[act[a2]], __ldg(T0 + (size_t)act[a2] * dc0 + 1 + c), s2);
+                        for (int j2 = 0; j2 < ntouched; ++j2) {
+                            const int r = touched[j2];
+                            s2 = fma(cs[r], __ldg(T0 + (size_t)r * dc0 + 1 + c), s2);
                         }
                         zs[c] = s2;
                     }
@@ -390,10 +405,10 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                         double s2 = -__ldg(g);
                         for (int c = 0; c < nf; ++c) s2 = fma(__ldg(g + 1 + c), zs[c], s2);
                         v[rr] = s2;
-                        worst = fmax(worst, isA[rr] ? fabs(s2) : s2);
+                        worst = dmax2(worst, isA[rr] ? fabs(s2) : s2);
                     }
                 }
-                worst = warp_max_nonneg(fmax(worst, 0.0));
+                worst = warp_max_nonneg(dmax2(worst, 0.0));
                 if (worst <= PPG_FEAS_TOL) { feasible = true; break; }
                 if (++rechecks > 3) break;
                 if (lane < k) cs[act[lane]] = 0.0;  // active-row slots of cs are only borrowed for the verification
@@ -403,19 +418,19 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
             int irow = 0x7fffffff;
 #pragma unroll
             for (int rr = RPL - 1; rr >= 0; --rr) {
-                const unsigned m = __ballot_sync(PPG_FULL, !isA[rr] && rr * 32 + lane < R0 && v[rr] == wmax);
+                const unsigned m = __ballot_sync(PPG_FULL, use[rr] && v[rr] == wmax);
                 if (m) irow = rr * 32 + __ffs((int)m) - 1;
             }
             ++n_it;
             double g2[KC];
 #pragma unroll
-            for (int a = 0; a < KC; ++a) g2[a] = (a < k) ? __ldg(Gam + (size_t)actr[a] * R0 + irow) : 0.0;  // broadcast loads
+            for (int a = 0; a < KC; ++a) g2[a] = __ldg(growA[a] + irow);  // broadcast loads (padded slots: M == 0)
+            const double* __restrict__ gi = Gam + (size_t)irow * R0;
             double c2[RPL];
             double mycol = 0.0;
 #pragma unroll
             for (int rr = 0; rr < RPL; ++rr) {
-                const int r = rr * 32 + lane;
-                double x2 = (r < R0) ? __ldg(Gam + (size_t)irow * R0 + r) : 0.0;
+                double x2 = __ldg(gi + rcl[rr]);
 #pragma unroll
                 for (int a = 0; a < KC; ++a) x2 = fma(-M[rr][a], g2[a], x2);
                 c2[rr] = x2;
@@ -424,15 +439,21 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
             const double nn = shfl_d(mycol, irow & 31);   // |N g_i|^2
             if (!(nn > 1e-12)) break;                      // row i lies in the span of the active rows: leave it to the LP
             // the relaxation parameter needs no accuracy: fp32 reciprocal
-            const double tau = (K2A_OMEGA * wmax) * (double)__frcp_rn((float)nn);
+            const double tau = (K2A_OMEGA * wmax) * (double)rcp_approx((float)nn);
 #pragma unroll
             for (int rr = 0; rr < RPL; ++rr) v[rr] = fma(-tau, c2[rr], v[rr]);
             // z -= tau (g_i - G_A' w),  w = Sinv ga: lane a accumulates the coefficient of its active row
-            if (lane == 0) cs[irow] -= tau;
             {
+                const double old = cs[irow];      // broadcast read; the row list only grows on a first visit
+                __syncwarp();
+                if (lane == 0) {
+                    if (old == 0.0) touched[ntouched] = irow;
+                    cs[irow] = old - tau;
+                }
+                if (old == 0.0) ++ntouched;
                 double wa = 0.0;
 #pragma unroll
-                for (int b = 0; b < KC; ++b) wa = fma(Sinv[(lane < KC ? lane : 0) * KC + b], g2[b], wa);
+                for (int b2 = 0; b2 < KC; ++b2) wa = fma(srow[b2], g2[b2], wa);
                 if (lane < k) cA = fma(tau, wa, cA);
             }
         }
@@ -453,7 +474,7 @@ static cudaError_t launch_k2a_small(const DevProgram& P, const uint64_t* masks, 
                                     unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count,
                                     cudaStream_t st) {
     auto kern = k2a_relax_small_kernel<RPL, KC>;
-    const size_t per_warp = (size_t)KC * KC + KC + (size_t)P.R0 + (size_t)P.nfree + (size_t)(KC / 2 + 1);
+    const size_t per_warp = (size_t)KC * KC + KC + (size_t)P.R0 + (size_t)P.nfree + (size_t)(KC / 2 + 1) + (size_t)(P.R0 / 2 + 1);
     const size_t smem = per_warp * 4 * sizeof(double);
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem);
