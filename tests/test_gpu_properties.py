@@ -159,3 +159,23 @@ def test_status_bytes_stay_on_device_and_counters_move():
     assert c['k2_lps'] > 0 and c['k2_pivots'] > c['k2_lps'] and c['k4_lps'] > 0 and sol.gpu_launches > 10
     assert len(sol.critical_regions) == 7
     eng.close()
+
+
+@pytest.mark.parametrize('name', ['mpc_n5', 'rand_6_3_12_s1', 'transport_mplp', 'portfolio_analog', 'ctrl_alloc_n2'])
+def test_relaxation_certificates_never_change_a_decision(name):
+    """K2a only certifies feasibility (exactly re-verified point); with it disabled (stage bit 8) the simplex alone must
+    produce the same status bytes on every golden candidate"""
+    engine, prog, eng = _engine(name)
+    g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
+    ne = int(g['n_eq'])
+    for lv in range(int(g['n_levels'])):
+        cands = g[f'level{lv}_candidates'].tolist()
+        masks = eng.masks_from_lists(cands)
+        k_act = len(cands[0]) - ne
+        with_k2a = eng.level_eval(masks, k_act, stages=3).cpu().numpy()
+        without = eng.level_eval(masks, k_act, stages=3 | 8).cpu().numpy()
+        assert numpy.array_equal(with_k2a & 3, without & 3), f'{name} level {lv + 1}'
+        assert numpy.array_equal(with_k2a & 3, g[f'level{lv}_status'] & 3)
+    c = eng.counters()
+    assert c['k2a_tried'] > 0 and c['k2a_certified'] <= c['k2a_tried']
+    eng.close()
