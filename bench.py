@@ -14,9 +14,11 @@ L = 3 in any reasonable time).  A "step" is one full pass of the l
           in HBM.  CUDA events on the launch stream, max over ranks, L2 flushed between steps.
   e2e     the same pass through the public call solve_mpqp(program, mpqp_algorithm.combinatorial) with HOST numpy
           program data: upload, all kernels, download of the region matrices, CriticalRegion objects built.
-  roofline  dominant kernel K2 (feasibility LP): useful fp64 flops (2 x pivots x live rows x columns, counted in-kernel)
-          / its summed launch durations (CUDA events recorded around each launch inside libppgpu), against the fp64 FMA
-          peak measured on this device by a register-resident DFMA loop (MEASURED_PEAKS.json has no fp64 entry).
+  roofline  the kernel family with the largest share of the step (K2a feasibility certificates since round 1 v5; K2
+          simplex before): useful fp64 flops counted in-kernel (K2a: 2 x steps x R0 x (1+k'); K2: 2 x pivots x live rows
+          x columns) / its summed launch durations (CUDA events recorded around each launch inside libppgpu), against
+          the fp64 FMA peak measured on this device by a register-resident DFMA loop (MEASURED_PEAKS.json has no fp64
+          entry).  The path is fp64-FMA / latency bound, not HBM bound: 8W+2 algorithmic bytes per candidate.
   cpu_baseline  the oracle (numpy/HiGHS port of the reference's per-candidate path) on all host cores over a bounded
           random sample of level-3 candidates of the same program.
 """
@@ -240,10 +242,16 @@ def run_gpu(args, rank, world, local_rank):
         return
     value = units * len(ms_dev) / (sum(ms_dev) * 1e-3)
     e2e_value = units * len(ms_e2e) / (sum(ms_e2e) * 1e-3)
-    k2 = prof['k2_feas_lp']
-    k2_flops = 2.0 * counters['k2_work']
+    # dominant kernel family of the timed steps and its in-kernel count of useful fp64 FMAs
+    fams = {'k2a_relax': ('k2a_relax_small_kernel (feasibility certificates)', counters['k2a_work'], counters['k2a_tried']),
+            'k2_feas_lp': ('k2_feas_kernel (feasibility simplex)', counters['k2_work'], counters['k2_lps']),
+            'k34_kkt_cheb': ('k34_kernel (KKT + Chebyshev screen)', counters['k4_work'], counters['k4_lps'])}
+    dom = max(fams, key=lambda f: prof[f]['ms'])
+    k2 = prof[dom]
+    dom_name, dom_work, dom_units = fams[dom]
+    k2_flops = 2.0 * dom_work
     k2_tflops = k2_flops / max(k2['ms'] * 1e-3, 1e-12) / 1e12
-    hbm_bytes = 25.0 * counters['k2_lps']  # ~25 B per candidate (mask in, status in/out)
+    hbm_bytes = (8.0 * eng.W + 2.0) * dom_units  # mask in, status byte in + out
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -265,15 +273,18 @@ def run_gpu(args, rank, world, local_rank):
         'e2e': {'value': e2e_value, 'unit': 'candidates/s', 'ms_per_step': sum(ms_e2e) / len(ms_e2e),
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'call': 'solve_mpqp(program, combinatorial)'},
         'gpu_launches': int(total_launches.item()),
-        'roofline': {'kernel': 'k2_feas_kernel', 'bound': 'fp64', 'achieved': k2_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+        'roofline': {'kernel': dom_name, 'bound': 'fp64', 'achieved': k2_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                      'frac': k2_tflops / fp64_peak if fp64_peak else None, 'traffic': traffic,
                      'peak_source': 'measured on this device: register-resident DFMA loop (ppgpu_measure_fp64_peak); '
                                     'MEASURED_PEAKS.json carries no fp64 figure',
                      'launches': k2['launches'], 'avg_launch_ms': k2['ms'] / max(1, k2['launches']),
-                     'flops_per_launch': k2_flops / max(1, k2['launches']), 'lps': counters['k2_lps'],
-                     'pivots': counters['k2_pivots'],
+                     'flops_per_launch': k2_flops / max(1, k2['launches']), 'units': dom_units,
+                     'share_of_step': k2['ms'] / max(1e-9, sum(v['ms'] for v in prof.values())),
+                     'flop_model': 'useful fp64 FMAs counted in-kernel: K2a steps x R0 x (1+k); K2/K4 pivots x live rows x columns',
+                     'k2a': {'tried': counters['k2a_tried'], 'certified': counters['k2a_certified'], 'steps': counters['k2a_steps']},
+                     'k2': {'lps': counters['k2_lps'], 'pivots': counters['k2_pivots']},
                      'hbm': {'achieved': hbm_bytes / max(k2['ms'] * 1e-3, 1e-12) / 1e9, 'peak': peaks.get('hbm_gbs'),
-                             'unit': 'GB/s', 'note': 'algorithmic bytes are ~25 B per candidate: not HBM bound'}},
+                             'unit': 'GB/s', 'note': 'algorithmic bytes are 8W+2 B per candidate: not HBM bound'}},
         'kernels_ms_per_step': {k: v['ms'] / len(ms_dev) for k, v in prof.items() if v['launches']},
         'clocks': sampler.summary(),
         'fp64_peak_tflops': fp64_peak,

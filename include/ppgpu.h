@@ -48,7 +48,7 @@ typedef struct {
 } ppgpu_info;
 
 /* number of uint64 counters returned by ppgpu_counters */
-#define PPGPU_NUM_COUNTERS 16
+#define PPGPU_NUM_COUNTERS 24
 
 const char* ppgpu_last_error(void);
 int ppgpu_version(void);

@@ -31,8 +31,9 @@ enum Counter {
     CNT_K4_LPS, CNT_K4_PIVOTS, CNT_K4_WORK,
     CNT_K5_LPS, CNT_K5_PIVOTS, CNT_K5_WORK,
     CNT_NUMERIC, CNT_BORDER, CNT_K6_LOOKUPS,
-    CNT_K2A_TRIED, CNT_K2A_CERTIFIED, CNT_K2A_STEPS,
-    CNT_COUNT = 16
+    CNT_K2A_TRIED, CNT_K2A_CERTIFIED, CNT_K2A_STEPS,  // 13, 14, 15
+    CNT_K2A_WORK,                                     // 16: steps x R0 x (1 + k') useful FMAs
+    CNT_COUNT = 24
 };
 
 __device__ __forceinline__ bool mask_test(const uint64_t* m, int i) { return (m[i >> 6] >> (i & 63)) & 1ull; }

@@ -208,6 +208,7 @@ k2a_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
         atomicAdd(&counters[CNT_K2A_TRIED], n_try);
         atomicAdd(&counters[CNT_K2A_CERTIFIED], n_ok);
         atomicAdd(&counters[CNT_K2A_STEPS], n_it);
+        atomicAdd(&counters[CNT_K2A_WORK], n_it * (unsigned long long)(R0 * (k + 1)));
     }
 }
 
@@ -466,6 +467,7 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
         atomicAdd(&counters[CNT_K2A_TRIED], n_try);
         atomicAdd(&counters[CNT_K2A_CERTIFIED], n_ok);
         atomicAdd(&counters[CNT_K2A_STEPS], n_it);
+        atomicAdd(&counters[CNT_K2A_WORK], n_it * (unsigned long long)(R0 * (k + 1)));
     }
 }
 
