@@ -364,9 +364,9 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                     M[rr][a] = (a < k) ? m2 : 0.0;
                     s2 = fma(gA[a], w0[a], s2);
                 }
-                v[rr] = s2;
                 isA[rr] = r < P.mi && mask_test(mk, r);
                 use[rr] = r < R0 && !isA[rr];
+                v[rr] = use[rr] ? s2 : -1e300;   // parked: never the maximum, never updated meaningfully
                 if (r < R0) cs[r] = 0.0;
             }
         }
@@ -376,7 +376,7 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
         for (int it = 0; it < max_iter; ++it) {
             double lv = 0.0;
 #pragma unroll
-            for (int rr = 0; rr < RPL; ++rr) lv = dmax2(lv, use[rr] ? v[rr] : 0.0);
+            for (int rr = 0; rr < RPL; ++rr) lv = dmax2(lv, v[rr]);
             const double wmax = warp_max_nonneg(lv);
             if (wmax <= PPG_FEAS_TOL) {
                 // ---- exact verification: materialise z from the coefficients, recompute every near-binding row
@@ -401,11 +401,11 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
 #pragma unroll
                 for (int rr = 0; rr < RPL; ++rr) {
                     const int r = rr * 32 + lane;
-                    if (r < R0 && (isA[rr] || v[rr] > -1e-3)) {  // far-from-binding rows cannot be off by 1e-3 (error <= ~1e-7)
+                    if (r < R0 && (isA[rr] || v[rr] > -1e-3)) {  // (parked rows hold -1e300: only isA brings them in)  // far-from-binding rows cannot be off by 1e-3 (error <= ~1e-7)
                         const double* g = T0 + (size_t)r * dc0;
                         double s2 = -__ldg(g);
                         for (int c = 0; c < nf; ++c) s2 = fma(__ldg(g + 1 + c), zs[c], s2);
-                        v[rr] = s2;
+                        v[rr] = isA[rr] ? -1e300 : s2;
                         worst = dmax2(worst, isA[rr] ? fabs(s2) : s2);
                     }
                 }
@@ -416,12 +416,12 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                 __syncwarp();
                 continue;
             }
-            int irow = 0x7fffffff;
+            int myslot = -1;
 #pragma unroll
-            for (int rr = RPL - 1; rr >= 0; --rr) {
-                const unsigned m = __ballot_sync(PPG_FULL, use[rr] && v[rr] == wmax);
-                if (m) irow = rr * 32 + __ffs((int)m) - 1;
-            }
+            for (int rr = RPL - 1; rr >= 0; --rr) if (v[rr] == wmax) myslot = rr;
+            const int wl = __ffs((int)__ballot_sync(PPG_FULL, myslot >= 0)) - 1;   // any most-violated row will do
+            const int wslot = __shfl_sync(PPG_FULL, myslot, wl);
+            const int irow = wslot * 32 + wl;
             ++n_it;
             double g2[KC];
 #pragma unroll
@@ -435,9 +435,9 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
 #pragma unroll
                 for (int a = 0; a < KC; ++a) x2 = fma(-M[rr][a], g2[a], x2);
                 c2[rr] = x2;
-                if (rr == (irow >> 5)) mycol = x2;
+                if (rr == wslot) mycol = x2;
             }
-            const double nn = shfl_d(mycol, irow & 31);   // |N g_i|^2
+            const double nn = shfl_d(mycol, wl);   // |N g_i|^2
             if (!(nn > 1e-12)) break;                      // row i lies in the span of the active rows: leave it to the LP
             // the relaxation parameter needs no accuracy: fp32 reciprocal
             const double tau = (K2A_OMEGA * wmax) * (double)rcp_approx((float)nn);
