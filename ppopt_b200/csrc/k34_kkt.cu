@@ -22,10 +22,109 @@
 
 namespace ppgpu {
 
+
+// K3p - one THREAD per feasible candidate (small k'): Schur system + multiplier-sign test entirely in registers.
+// The warp-per-candidate kernel below spent 85 % of its instructions here with ~11 of 32 lanes active; this stage has
+// no cross-lane work at all, so 32 candidates share one instruction stream.  Survivors get PPG_ST_PRE and are the
+// only ones k34_kernel still builds rows / runs the Chebyshev LP for.
+template <int KC>
+__global__ void __launch_bounds__(128)
+k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k, uint8_t* __restrict__ status) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const uint8_t st = status[idx];
+    if (!(st & PPG_ST_FEAS)) return;
+    const int t = P.t, t1 = P.t + 1, mi = P.mi, W = P.W;
+    const uint64_t* mk = masks + idx * W;
+    int act[KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a) act[a] = (a < k) ? mask_nth(mk, W, a) : 0;
+    double L[KC][KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) L[a][b] = (a < k && b < k) ? __ldg(P.G + (size_t)act[a] * mi + act[b]) : (a == b ? 1.0 : 0.0);
+    bool pd = true;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+        double d = L[j][j];
+#pragma unroll
+        for (int c = 0; c < j; ++c) d = fma(-L[j][c], L[j][c], d);
+        if (!(d > 0.0)) pd = false;
+        const double sd = sqrt(d > 0.0 ? d : 1.0), isd = 1.0 / sd;
+        L[j][j] = sd;
+#pragma unroll
+        for (int i = j + 1; i < KC; ++i) {
+            double s2 = L[i][j];
+#pragma unroll
+            for (int c = 0; c < j; ++c) s2 = fma(-L[i][c], L[j][c], s2);
+            L[i][j] = s2 * isd;
+        }
+    }
+    if (!pd) { status[idx] = st | PPG_ST_PRE; return; }  // let the warp kernel report the numeric failure
+    bool reject = false;
+    // one right-hand side (column of V) at a time keeps the register footprint at KC doubles
+    double ub[KC], mx[KC], mag[KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a) { ub[a] = 0.0; mx[a] = 0.0; mag[a] = 0.0; }
+    for (int c = 0; c < t1; ++c) {
+        double x[KC];
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            double s2 = (i < k) ? -__ldg(P.V + (size_t)act[i] * t1 + c) : 0.0;
+#pragma unroll
+            for (int j = 0; j < i; ++j) s2 = fma(-L[i][j], x[j], s2);
+            x[i] = s2 / L[i][i];
+        }
+#pragma unroll
+        for (int i = KC - 1; i >= 0; --i) {
+            double s2 = x[i];
+#pragma unroll
+            for (int j = i + 1; j < KC; ++j) s2 = fma(-L[j][i], x[j], s2);
+            x[i] = s2 / L[i][i];
+        }
+        if (c == 0) {
+#pragma unroll
+            for (int a = 0; a < KC; ++a) { ub[a] = x[a]; mag[a] = fabs(x[a]); }
+        } else {
+            const double lo = __ldg(P.th_lo + c - 1), hi = __ldg(P.th_hi + c - 1);
+#pragma unroll
+            for (int a = 0; a < KC; ++a) {
+                const double av = x[a];
+                mx[a] = fmax(mx[a], fabs(av));
+                if (av != 0.0) { const double term = fmax(av * lo, av * hi); ub[a] += term; mag[a] += fabs(term); }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < KC; ++a)
+        if (a < k && mx[a] > PPG_ZERO_ROW && ub[a] < -1e-9 * fmax(1.0, mag[a])) reject = true;
+    (void)t;
+    if (!reject) status[idx] = st | PPG_ST_PRE;
+}
+
+template <int KC>
+static cudaError_t launch_k3p_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status, cudaStream_t st) {
+    k3_prefilter_kernel<KC><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, masks, n, k_act, status);
+    return cudaGetLastError();
+}
+
+// returns true (and launches) when the thread-per-candidate prefilter covers this level
+static bool launch_k3p(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status, cudaStream_t st,
+                       cudaError_t* err) {
+    *err = cudaSuccess;
+    if (k_act < 1 || k_act > 8) return false;
+    if (k_act <= 2) *err = launch_k3p_t<2>(P, masks, n, k_act, status, st);
+    else if (k_act <= 4) *err = launch_k3p_t<4>(P, masks, n, k_act, status, st);
+    else if (k_act <= 6) *err = launch_k3p_t<6>(P, masks, n, k_act, status, st);
+    else *err = launch_k3p_t<8>(P, masks, n, k_act, status, st);
+    return true;
+}
+
 template <int RPT, int DC, int WPC>
 __global__ void __launch_bounds__(32 * WPC)
 k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
-           unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters) {
+           unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int use_pre) {
     typedef LpCore<1, RPT, DC> Core;
     extern __shared__ double dyn_smem[];
     __shared__ typename Core::Shared sh_all[WPC];
@@ -43,8 +142,12 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
         if (lane == 0) v = atomicAdd(queue, 1ull);
         const long long idx = (long long)__shfl_sync(PPG_FULL, v, 0);
         if (idx >= n) break;
-        const uint8_t st = status[idx];
+        uint8_t st = status[idx];
         if (!(st & PPG_ST_FEAS)) continue;
+        if (use_pre) {
+            if (!(st & PPG_ST_PRE)) continue;   // rejected by the thread-per-candidate prefilter
+            st &= (uint8_t)~PPG_ST_PRE;
+        }
         const uint64_t* mk = masks + idx * W;
         const int k = kmax;
         __syncwarp();
@@ -104,6 +207,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
                 if (mx > PPG_ZERO_ROW && ub < -1e-9 * fmax(1.0, mag)) reject = true;
             }
             if (__any_sync(PPG_FULL, reject)) {
+                if (use_pre && lane == 0) status[idx] = st;
                 continue;  // not optimal: status keeps PPG_ST_FEAS only
             }
             // region rows straight into the tableau registers: T[.][0] = f, T[.][1..t] = a, T[.][t+1] = 1 (the s column)
@@ -197,7 +301,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
             uint8_t s2 = st;
             if (pass) s2 |= PPG_ST_OPT;
             if (numeric) { s2 |= PPG_ST_NUMERIC; n_num++; }
-            if (s2 != st) status[idx] = s2;
+            if (s2 != st || use_pre) status[idx] = s2;
         }
     }
     if (lane == 0 && (n_lp || n_num)) {
@@ -210,7 +314,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
 
 template <int RPT, int DC>
 static cudaError_t launch_k34_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
-                                unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st) {
+                                unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, int use_pre) {
     constexpr int WPC = 4;
     auto kern = k34_kernel<RPT, DC, WPC>;
     const size_t per_warp = (size_t)k_act * k_act + (size_t)k_act * (P.t + 1) + (size_t)((k_act + 1) / 2 + 1);
@@ -228,19 +332,22 @@ static cudaError_t launch_k34_t(const DevProgram& P, const uint64_t* masks, long
     const long long need = (n + WPC - 1) / WPC;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 32 * WPC, smem, st>>>(P, masks, n, k_act, status, queue, counters);
+    kern<<<(unsigned)grid, 32 * WPC, smem, st>>>(P, masks, n, k_act, status, queue, counters, use_pre);
     return cudaGetLastError();
 }
 
 #define K34_RPT_SWITCH(DCV)                                                                                  \
-    if (P.R0 <= 32) return launch_k34_t<1, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st);  \
-    if (P.R0 <= 64) return launch_k34_t<2, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st);  \
-    if (P.R0 <= 128) return launch_k34_t<4, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st); \
-    if (P.R0 <= 256) return launch_k34_t<8, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st); \
+    if (P.R0 <= 32) return launch_k34_t<1, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st, use_pre);  \
+    if (P.R0 <= 64) return launch_k34_t<2, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st, use_pre);  \
+    if (P.R0 <= 128) return launch_k34_t<4, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st, use_pre); \
+    if (P.R0 <= 256) return launch_k34_t<8, DCV>(P, masks, n, k_act, status, queue, counters, sm_count, st, use_pre); \
     return cudaErrorInvalidValue;
 
 cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st) {
+    cudaError_t perr;
+    const int use_pre = launch_k3p(P, masks, n, k_act, status, st, &perr) ? 1 : 0;
+    if (perr != cudaSuccess) return perr;
     if (P.t + 2 <= 8) { K34_RPT_SWITCH(8) }
     if (P.t + 2 <= 16) { K34_RPT_SWITCH(16) }
     return cudaErrorInvalidValue;

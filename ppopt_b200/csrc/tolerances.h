@@ -41,6 +41,7 @@
 #define PPG_ST_BORDER 16u   // a decision fell inside a borderline band (reported, never silently ignored)
 #define PPG_ST_NUMERIC 32u  // iteration limit / singular KKT / non-finite value
 #define PPG_ST_UNBOUNDED 64u  // LP unbounded (reference backend would answer "not optimal")
+#define PPG_ST_PRE 128u       // transient: passed the K3 thread-per-candidate prefilter (cleared by k34_kernel)
 
 // LP return codes
 #define PPG_LP_OPTIMAL 0
