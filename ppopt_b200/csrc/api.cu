@@ -105,7 +105,7 @@ int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, 
     D.mi = R.mi; D.np = R.np; D.W = R.W; D.R0 = R.R0; D.nfree = R.nfree; D.use_gram = R.use_gram;
     D.dc0 = R.nfree + 2;
 #define UP(field, vecname) if ((e = upload(p, R.vecname, &D.field)) != cudaSuccess) { ppgpu_program_destroy(p); return fail("upload " #field, e); }
-    UP(At, At) UP(T0, T0) UP(Gam, Gam) UP(G, G) UP(V, V) UP(th_lo, th_lo) UP(th_hi, th_hi) UP(A, A) UP(b, b) UP(F, F) UP(A_t, At_theta) UP(b_t, bt) UP(Q, Q) UP(c, c) UP(H, H)
+    UP(At, At) UP(C1, C1) UP(T0, T0) UP(Gam, Gam) UP(G, G) UP(V, V) UP(th_lo, th_lo) UP(th_hi, th_hi) UP(A, A) UP(b, b) UP(F, F) UP(A_t, At_theta) UP(b_t, bt) UP(Q, Q) UP(c, c) UP(H, H)
 #undef UP
     void* dc = nullptr;
     if ((e = cudaMalloc(&dc, (CNT_COUNT + QUEUE_SLOTS) * sizeof(unsigned long long))) != cudaSuccess) {
@@ -160,6 +160,7 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
         ProfScope ps(p, st, 0);
         e = launch_k1(p->dev, d_masks, n, k_act, d_status, p->d_counters, p->sm_count, st);
         if (e != cudaSuccess) return fail("K1 rank", e);
+        if (k_act >= 1 && k_act <= 8) p->launches++;  // prefilter + QR
         p->launches++;
     }
     if ((stages & 2) && !(stages & 8)) {
@@ -183,6 +184,7 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
         ProfScope ps(p, st, 2);
         if (p->dev.is_qp && p->dev.use_gram) {
             e = launch_k34(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st);
+            if (k_act >= 1 && k_act <= 8) p->launches++;  // the thread-per-candidate prefilter is a launch of its own
         } else {
             e = launch_mark_general(p->dev, n, k_act, d_status, st);
         }

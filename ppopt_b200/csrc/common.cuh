@@ -14,6 +14,7 @@ struct DevProgram {
     int mi, np, W, R0, nfree, use_gram;
     int dc0;  // row stride of T0 = nfree + 2
     const double* At;   // mi x np      reduced inequality rows (K1)
+    const double* C1;   // mi x mi      correlation matrix of the reduced rows (K1 prefilter)
     const double* T0;   // R0 x dc0     base feasibility tableau [rhs | v | theta | s] (K2)
     const double* Gam;  // R0 x R0      Gram of the feasibility rows (K2a relaxation certificates)
     const double* G;    // mi x mi      Gram  At Qr^-1 At'  (K3)

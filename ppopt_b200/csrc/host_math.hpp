@@ -30,6 +30,8 @@ struct ReducedProgram {
     vec At;
     // K2: base tableau rows (R0 x (nfree + 2)), column layout [rhs | v(np) | theta(t) | s]
     vec T0;
+    // K1p: correlation matrix of the reduced rows  C1[i][j] = <At_i, At_j> / (|At_i| |At_j|)  (0 for null rows)
+    vec C1;
     // K2a: Gram of the feasibility rows  Gam = Gf Gf' (R0 x R0), Gf = T0[:, 1..nfree]
     vec Gam;
     // K3: Gram G (mi x mi) and V (mi x (t+1)) with layout [const | theta coefficients]
@@ -169,6 +171,22 @@ inline bool reduce_program(int n, int t, int m, int q, int ne, int is_qp, const 
         r[0] = b_t[i];
         for (int j = 0; j < t; ++j) r[1 + np + j] = A_t[(size_t)i * t + j];
         r[1 + np + t] = 1.0;
+    }
+    P.C1.assign((size_t)mi * mi, 0.0);
+    {
+        vec nr(mi, 0.0);
+        for (int i = 0; i < mi; ++i) {
+            double s = 0.0;
+            for (int c = 0; c < np; ++c) s += P.At[(size_t)i * np + c] * P.At[(size_t)i * np + c];
+            nr[i] = std::sqrt(s);
+        }
+        for (int i = 0; i < mi; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double s = 0.0;
+                for (int c = 0; c < np; ++c) s += P.At[(size_t)i * np + c] * P.At[(size_t)j * np + c];
+                const double v = (nr[i] > 0.0 && nr[j] > 0.0) ? s / (nr[i] * nr[j]) : 0.0;
+                P.C1[(size_t)i * mi + j] = P.C1[(size_t)j * mi + i] = v;
+            }
     }
     P.Gam.assign((size_t)P.R0 * P.R0, 0.0);
     for (int i = 0; i < P.R0; ++i)

@@ -118,12 +118,55 @@ static cudaError_t launch_k1_t(const DevProgram& P, const uint64_t* masks, long 
 }
 
 
+
+// K1p - one THREAD per candidate: unpivoted Cholesky of the k' x k' correlation block C1[act,act] in registers.
+// If every Schur pivot d_j (= sin^2 of the angle between row j and the span of the rows before it) exceeds
+// PPG_RANK_PRE = 1e-2, then det >= 1e-2^(k'-1), hence sigma_min^2 >= det / k'^(k'-1) >= 4.8e-21 for k' <= 8, far above
+// numpy's rank threshold (sigma_max * max(k,n) * eps)^2 ~ 4e-28: the candidate is full rank, PPG_ST_RANK is set and
+// the QR kernel skips it.  Everything else (2 % of the candidates, among them every truly deficient set) is handed to
+// the column-pivoted QR below through PPG_ST_PRE.  The prefilter never declares a deficiency.
+#define PPG_RANK_PRE 1e-2
+template <int KC>
+__global__ void __launch_bounds__(128)
+k1_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k, uint8_t* __restrict__ status) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int mi = P.mi, W = P.W;
+    const uint64_t* mk = masks + idx * W;
+    int act[KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a) act[a] = (a < k) ? mask_nth(mk, W, a) : 0;
+    double L[KC][KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) L[a][b] = (a < k && b < k) ? __ldg(P.C1 + (size_t)act[a] * mi + act[b]) : (a == b ? 1.0 : 0.0);
+    bool clear = k <= P.np;
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+        double d = L[j][j];
+#pragma unroll
+        for (int c = 0; c < j; ++c) d = fma(-L[j][c], L[j][c], d);
+        if (!(d > PPG_RANK_PRE)) clear = false;
+        const double isd = rsqrt(d > PPG_RANK_PRE ? d : 1.0);
+        L[j][j] = 1.0;
+#pragma unroll
+        for (int i = j + 1; i < KC; ++i) {
+            double s2 = L[i][j];
+#pragma unroll
+            for (int c = 0; c < j; ++c) s2 = fma(-L[i][c], L[j][c], s2);
+            L[i][j] = s2 * isd;
+        }
+    }
+    status[idx] = clear ? PPG_ST_RANK : PPG_ST_PRE;
+}
+
 // Small active sets (k' <= 16): GS = 4/8/16 lanes per candidate, 32/GS candidates per warp.  Every lane of the warp
 // runs the same k' Householder steps (uniform shuffles); a group that has already decided just stops updating.
 template <int NP, int GS>
 __global__ void __launch_bounds__(128)
 k1_rank_group_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k, uint8_t* __restrict__ status,
-                     unsigned long long* __restrict__ counters) {
+                     unsigned long long* __restrict__ counters, int use_pre) {
     constexpr int CPW = 32 / GS;
     const int lane = threadIdx.x & 31, gl = lane % GS, gid = lane / GS, gbase = gid * GS;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -132,7 +175,11 @@ k1_rank_group_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
     unsigned long long n_border = 0;
     for (long long base = warp0 * CPW; base < n; base += nwarps * CPW) {
         const long long idx = base + gid;
-        const bool valid = idx < n;
+        bool valid = idx < n;
+        if (use_pre) {
+            valid = valid && (status[idx] & PPG_ST_PRE);   // cleared candidates already carry PPG_ST_RANK
+            if (!__any_sync(PPG_FULL, valid)) continue;
+        }
         const uint64_t* mk = masks + (valid ? idx : 0) * W;
         double col[NP];
         bool done = !(valid && gl < k);
@@ -201,23 +248,32 @@ k1_rank_group_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
 
 template <int NP, int GS>
 static cudaError_t launch_k1_g(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
-                               unsigned long long* counters, int sm_count, cudaStream_t st) {
+                               unsigned long long* counters, int sm_count, cudaStream_t st, int use_pre) {
     const int threads = 128;
     const long long per_block = (threads / 32) * (32 / GS);
     long long blocks = (n + per_block - 1) / per_block;
     const long long cap = (long long)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k1_rank_group_kernel<NP, GS><<<(unsigned)blocks, threads, 0, st>>>(P, masks, n, k_act, status, counters);
+    k1_rank_group_kernel<NP, GS><<<(unsigned)blocks, threads, 0, st>>>(P, masks, n, k_act, status, counters, use_pre);
     return cudaGetLastError();
 }
 
 template <int NP>
 static cudaError_t launch_k1_np(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                                 unsigned long long* counters, int sm_count, cudaStream_t st) {
-    if (k_act >= 1 && k_act <= 4) return launch_k1_g<NP, 4>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (k_act >= 1 && k_act <= 8) return launch_k1_g<NP, 8>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (k_act >= 1 && k_act <= 16) return launch_k1_g<NP, 16>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (k_act >= 1 && k_act <= 8) {
+        const unsigned blocks = (unsigned)((n + 127) / 128);
+        if (k_act <= 2) k1_prefilter_kernel<2><<<blocks, 128, 0, st>>>(P, masks, n, k_act, status);
+        else if (k_act <= 4) k1_prefilter_kernel<4><<<blocks, 128, 0, st>>>(P, masks, n, k_act, status);
+        else if (k_act <= 6) k1_prefilter_kernel<6><<<blocks, 128, 0, st>>>(P, masks, n, k_act, status);
+        else k1_prefilter_kernel<8><<<blocks, 128, 0, st>>>(P, masks, n, k_act, status);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (k_act <= 4) return launch_k1_g<NP, 4>(P, masks, n, k_act, status, counters, sm_count, st, 1);
+        return launch_k1_g<NP, 8>(P, masks, n, k_act, status, counters, sm_count, st, 1);
+    }
+    if (k_act >= 1 && k_act <= 16) return launch_k1_g<NP, 16>(P, masks, n, k_act, status, counters, sm_count, st, 0);
     return launch_k1_t<NP, 1>(P, masks, n, k_act, status, counters, sm_count, st);
 }
 
