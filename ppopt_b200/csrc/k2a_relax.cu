@@ -373,6 +373,7 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
         __syncwarp();
         bool feasible = false;
         int rechecks = 0;
+        double wref = 0.0;
         for (int it = 0; it < max_iter; ++it) {
             double lv = 0.0;
 #pragma unroll
@@ -422,6 +423,12 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
             const int wl = __ffs((int)__ballot_sync(PPG_FULL, myslot >= 0)) - 1;   // any most-violated row will do
             const int wslot = __shfl_sync(PPG_FULL, myslot, wl);
             const int irow = wslot * 32 + wl;
+            // stall detector: a relaxation that has not halved its worst violation in 16 steps is not going to finish
+            // inside the budget (badly scaled or zero-margin sets; 0 of 1147 converging probes tripped it) -> simplex
+            if ((it & 15) == 0) {
+                if (it != 0 && wmax > 0.5 * wref) break;
+                wref = wmax;
+            }
             ++n_it;
             double g2[KC];
 #pragma unroll
@@ -498,8 +505,10 @@ static cudaError_t launch_k2a_small(const DevProgram& P, const uint64_t* masks, 
 cudaError_t launch_k2a(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count, cudaStream_t st) {
     if (k_act > 32 || P.nfree > 64) return cudaSuccess;  // outside the certificate kernel's envelope: K2 decides alone
-    if (k_act >= 1 && k_act <= 4 && P.R0 <= 128) { K2A_SMALL(4) }
-    if (k_act >= 5 && k_act <= 6 && P.R0 <= 128) { K2A_SMALL(6) }
+    if (k_act >= 1 && k_act <= 3 && P.R0 <= 128) { K2A_SMALL(3) }
+    if (k_act == 4 && P.R0 <= 128) { K2A_SMALL(4) }
+    if (k_act == 5 && P.R0 <= 128) { K2A_SMALL(5) }
+    if (k_act == 6 && P.R0 <= 128) { K2A_SMALL(6) }
     if (k_act >= 7 && k_act <= 8 && P.R0 <= 128) { K2A_SMALL(8) }
     if (P.R0 <= 32) return launch_k2a_t<1>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
     if (P.R0 <= 64) return launch_k2a_t<2>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
