@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../ppopt_b200/csrc/host_math.hpp"
@@ -115,20 +117,21 @@ LpResult lp_maxmin(Lp& lp, double thr, bool strict) {
         }
         if (j < 0) return {PPG_LP_OPTIMAL, beta};
         const double dir = (lp.colkind[j] == 1 && alpha[j] > 0.0) ? -1.0 : 1.0;
-        // ratio test: smallest rhs/a over rows with a > PPG_PIV_TOL; ties -> largest pivot, then smallest row
-        // (Bland mode: ties -> smallest basic variable id)
-        double tmin = INFINITY;
+        // Harris ratio test. Pass 1: largest step that keeps every basic slack >= -PPG_HARRIS (rows with entries down
+        // to PPG_TINY take part: ignoring a 5e-10 entry lets its row drift by 5e-10 x step ~ 1e-7). Pass 2: among the
+        // rows that block within that step take the LARGEST pivot (Bland mode: the smallest basic variable id).
+        double tmax = INFINITY;
         for (int i = 0; i < nr; ++i) {
             if (lp.rowflag[i] != 1) continue;
             const double a = dir * lp.at(i, j);
-            if (a > PPG_PIV_TOL) tmin = std::fmin(tmin, std::fmax(lp.at(i, 0), 0.0) * (1.0 / a));
+            if (a > PPG_TINY) tmax = std::fmin(tmax, (std::fmax(lp.at(i, 0), 0.0) + PPG_HARRIS) / a);
         }
-        if (tmin == INFINITY) return {PPG_LP_UNBOUNDED, INFINITY};
+        if (tmax == INFINITY) return {PPG_LP_UNBOUNDED, INFINITY};
         int r = -1; double bpiv = 0.0; int bvar = 1 << 30;
         for (int i = 0; i < nr; ++i) {
             if (lp.rowflag[i] != 1) continue;
             const double a = dir * lp.at(i, j);
-            if (a > PPG_PIV_TOL && std::fmax(lp.at(i, 0), 0.0) * (1.0 / a) <= tmin) {
+            if (a > PPG_TINY && std::fmax(lp.at(i, 0), 0.0) / a <= tmax) {
                 if (bland) { if (lp.bvar[i] < bvar) { bvar = lp.bvar[i]; r = i; } }
                 else if (a > bpiv) { bpiv = a; r = i; }
             }
@@ -445,6 +448,7 @@ int emit_region(Twin& tw, const std::vector<int>& act, double* laws_out, double*
             LpResult res = lp_maxmin(lp, margins_out ? 1e30 : -PPG_REDUND_TOL, false);
             tw.lp_pivots += lp.pivots;
             if (margins_out) margins_out[keep[a]] = res.beta;
+            if (margins_out && getenv("TWIN_DEBUG")) fprintf(stderr, "row %d code %d beta %.3e pivots %ld\n", keep[a], res.code, res.beta, lp.pivots);
             bool feas = res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED ||
                         (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_REDUND_TOL);
             if (feas) flags_out[keep[a]] |= 2;

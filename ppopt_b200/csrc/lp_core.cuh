@@ -116,6 +116,7 @@ struct LpShared {
     double c_ratio[2][NW];  // per-warp ratio-test winner: step length, effective pivot, rhs, row, basic-variable id
     double c_piv[2][NW];
     double c_inv[2][NW];
+    double c_hb[2][NW];     // per-warp Harris step bound (INF: the warp has no blocking row)
     double c_rhs[2][NW];
     int c_row[2][NW];
     int c_bvar[2][NW];
@@ -387,85 +388,82 @@ struct LpCore {
             }
             const bool entering_free = kj == 1;
             const double dir = (entering_free && aj > 0.0) ? -1.0 : 1.0;
-            // ---- ratio test inside the warp: min rhs/a, ties -> largest pivot (Bland: smallest basic id), then row
-            double colv[RPT];
-            float kf[RPT];
-            float lkf = CUDART_INF_F;
+            // ---- Harris ratio test, one barrier: every warp bounds the step with ITS rows ((rhs + delta) / a, entries down
+            // to PPG_TINY take part so that no row can drift by more than delta), pre-selects its largest pivot among
+            // the rows blocking within that bound and publishes (ratio, bound, pivot, row); after the barrier the global
+            // bound is the smallest published one and the winner is the largest pivot among the candidates that respect
+            // it (the warp that owns the global bound always has one).
+            double colv[RPT], rat[RPT];
+            double lh = CUDART_INF;
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 colv[rr] = dir * reg_pick<DC>(T[rr], j);
-                const bool ok = rflag[rr] == 1 && colv[rr] > PPG_PIV_TOL;
-                kf[rr] = ok ? __fdividef((float)fmax(T[rr][0], 0.0), (float)colv[rr]) : CUDART_INF_F;
-                lkf = fminf(lkf, kf[rr]);
+                rat[rr] = CUDART_INF;
+                if (rflag[rr] == 1 && colv[rr] > PPG_TINY) {
+                    const double ivc = 1.0 / colv[rr];
+                    const double rhs = T[rr][0] > 0.0 ? T[rr][0] : 0.0;
+                    rat[rr] = rhs * ivc;
+                    const double hb = (rhs + PPG_HARRIS) * ivc;
+                    lh = hb < lh ? hb : lh;
+                }
             });
-            const float wkf = __uint_as_float(__reduce_min_sync(PPG_FULL, __float_as_uint(lkf)));
+            const double wh = warp_min_nonneg(lh);
             int wrow = 0x7fffffff;
-            if (wkf != CUDART_INF_F) {
-                const float band = wkf * 1.00002f + 1e-30f;  // fp32 keys carry <= 4e-7 relative error: the true minimiser is inside
-                int ncl = 0, crow = 0x7fffffff;
+            if (wh != CUDART_INF) {
+                double lp = 0.0; int lrow = 0x7fffffff, lb = 0x7fffffff;
                 static_for<RPT>([&](auto RR) {
                     constexpr int rr = decltype(RR)::value;
-                    if (kf[rr] <= band) { ++ncl; crow = min(crow, rr * GT + tid); }
-                });
-                const unsigned m = __ballot_sync(PPG_FULL, ncl > 0);
-                const unsigned m2 = __ballot_sync(PPG_FULL, ncl > 1);
-                if ((m & (m - 1)) == 0u && m2 == 0u) {
-                    wrow = __shfl_sync(PPG_FULL, crow, __ffs((int)m) - 1);
-                } else {
-                    // several rows inside the band (degenerate vertex or a genuine near-tie): exact fp64 comparison
-                    double lr = CUDART_INF, lp = 0.0; int lrow = 0x7fffffff, lb = 0x7fffffff;
-                    static_for<RPT>([&](auto RR) {
-                        constexpr int rr = decltype(RR)::value;
-                        if (kf[rr] <= band) {
-                            const double ratio = fmax(T[rr][0], 0.0) * (1.0 / colv[rr]);
-                            const int row = rr * GT + tid;
-                            const bool better = ratio < lr || (ratio == lr && (bland ? bvar[rr] < lb : colv[rr] > lp));
-                            if (better) { lr = ratio; lp = colv[rr]; lrow = row; lb = bvar[rr]; }
-                        }
-                    });
-                    const double wr = warp_min_nonneg(lr);
-                    const bool el = lr == wr;
-                    if (bland) {
-                        const int wb = __reduce_min_sync(PPG_FULL, el ? lb : 0x7fffffff);
-                        wrow = __reduce_min_sync(PPG_FULL, (el && lb == wb) ? lrow : 0x7fffffff);
-                    } else {
-                        const double wp = warp_max_nonneg(el ? lp : 0.0);
-                        wrow = __reduce_min_sync(PPG_FULL, (el && lp == wp) ? lrow : 0x7fffffff);
+                    if (rat[rr] <= wh) {
+                        const int row = rr * GT + tid;
+                        const bool better = bland ? (bvar[rr] < lb) : (colv[rr] > lp);
+                        if (better) { lp = colv[rr]; lrow = row; lb = bvar[rr]; }
                     }
+                });
+                if (bland) {
+                    const int wb = __reduce_min_sync(PPG_FULL, lb);
+                    wrow = __reduce_min_sync(PPG_FULL, (lb == wb) ? lrow : 0x7fffffff);
+                } else {
+                    const double wp = warp_max_nonneg(lp);
+                    wrow = __reduce_min_sync(PPG_FULL, (lrow != 0x7fffffff && lp == wp) ? lrow : 0x7fffffff);
                 }
             }
-            // ---- the warp's winner publishes its row (+ exact ratio, 1/pivot); one barrier; everyone picks the global winner
             double* Pw = &sh.P[buf][warp][0];
             if (wrow == 0x7fffffff) {
-                if (lane == 0) sh.c_ratio[buf][warp] = CUDART_INF;
+                if (lane == 0) sh.c_hb[buf][warp] = CUDART_INF;
             } else if (tid == wrow % GT) {
                 static_for<RPT>([&](auto RR) {
                     constexpr int rr = decltype(RR)::value;
                     if (rr == wrow / GT) {
 #pragma unroll
                         for (int c = 0; c < DC; ++c) Pw[c] = T[rr][c];
-                        const double ivp = 1.0 / colv[rr];
                         sh.c_piv[buf][warp] = colv[rr];
-                        sh.c_inv[buf][warp] = ivp;
-                        sh.c_ratio[buf][warp] = fmax(T[rr][0], 0.0) * ivp;
+                        sh.c_inv[buf][warp] = 1.0 / colv[rr];
+                        sh.c_ratio[buf][warp] = rat[rr];
                         sh.c_bvar[buf][warp] = bvar[rr];
                         Pw[j] = dir * colv[rr] + 1.0;
                     }
                 });
+                sh.c_hb[buf][warp] = wh;
                 sh.c_row[buf][warp] = wrow;
             }
             gsync();
-            double gr = sh.c_ratio[buf][0]; int gw = 0;
+            double gt = sh.c_hb[buf][0];
             if constexpr (NW > 1) {
-                double gp = gr != CUDART_INF ? sh.c_piv[buf][0] : 0.0;
-                int gb = gr != CUDART_INF ? sh.c_bvar[buf][0] : 0x7fffffff;
 #pragma unroll
-                for (int w = 1; w < NW; ++w) {
+                for (int w = 1; w < NW; ++w) { const double h2 = sh.c_hb[buf][w]; gt = h2 < gt ? h2 : gt; }
+            }
+            if (gt == CUDART_INF) { out.code = PPG_LP_UNBOUNDED; out.beta = CUDART_INF; return out; }
+            int gw = 0; double gr = CUDART_INF;
+            {
+                double gp = -1.0; int gb = 0x7fffffff;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    if (sh.c_hb[buf][w] == CUDART_INF) continue;
                     const double r2 = sh.c_ratio[buf][w];
-                    if (r2 == CUDART_INF) continue;
+                    if (!(r2 <= gt)) continue;
                     const double p2 = sh.c_piv[buf][w];
                     const int b2 = sh.c_bvar[buf][w];
-                    const bool better = r2 < gr || (r2 == gr && (bland ? b2 < gb : p2 > gp));  // row order == warp order
+                    const bool better = bland ? (b2 < gb) : (p2 > gp);   // ties keep the lower warp = lower row
                     if (better) { gr = r2; gp = p2; gb = b2; gw = w; }
                 }
             }

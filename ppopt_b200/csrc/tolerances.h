@@ -23,8 +23,9 @@
 #define PPG_RADIUS_SCREEN 0.5e-8
 
 #define PPG_PIV_TOL 1e-9
-#define PPG_OPT_TOL 1e-9
+#define PPG_OPT_TOL 1e-12  // reduced-cost threshold: the objective error is tol x distance travelled (theta ranges of 1e2), so 1e-9 was too loose
 #define PPG_HARRIS 1e-9
+#define PPG_TINY 1e-12   // entries below this are treated as structural zeros in the ratio test
 #define PPG_DEGEN_STEP 1e-12
 #define PPG_BLAND_AFTER 8
 // column-pivoted QR: rank deficient iff |R_kk| <= PPG_RANK_TOL * |R_11|

@@ -179,3 +179,41 @@ def test_relaxation_certificates_never_change_a_decision(name):
     c = eng.counters()
     assert c['k2a_tried'] > 0 and c['k2a_certified'] <= c['k2a_tried']
     eng.close()
+
+
+@pytest.mark.parametrize('name', ['ctrl_alloc_n5', 'ctrl_alloc_n2', 'rand_6_3_12_s1'])
+def test_redundancy_flags_match_cpu_checker(name):
+    """K5's per-row keep/drop decisions (redundancy LPs with one row forced to equality) against the CPU checker, whose
+    LP margins are verified against HiGHS in tests/test_oracle.py.  Thin regions (radius ~1e-5, theta ranges ~1e2) make
+    this the most demanding accuracy test of the register simplex: a row may only differ if its margin sits within 2e-8
+    of the keep threshold."""
+    import torch
+    import twin_binding
+    engine, prog, eng = _engine(name)
+    path = os.path.join(GOLDEN, name + '.npz')
+    g = numpy.load(path)
+    tw = twin_binding.Twin.from_npz(path)
+    ne = int(g['n_eq'])
+    by_k = {}
+    for i in range(int(g['n_regions'])):
+        a = g[f'r{i}_active_set'].tolist()
+        by_k.setdefault(len(a) - ne, []).append(a)
+    n_rows = n_diff = 0
+    for k_act, asets in by_k.items():
+        masks = eng.masks_from_lists(asets)
+        status = torch.full((len(asets),), 7, dtype=torch.uint8, device=eng.tdev)
+        sel = torch.arange(len(asets), dtype=torch.int64, device=eng.tdev)
+        laws, rows, flags, info = [x.cpu().numpy() for x in eng.emit(masks, sel, k_act, status)]
+        for si, a in enumerate(asets):
+            rc, tl, tr, tf, ti, mg = tw.emit(tw.masks([a])[0], margins=True)
+            assert (info[si, 0] == 1.0) == (rc == 1)
+            if rc != 1 or eng.t == 1:
+                continue
+            assert numpy.array_equal(flags[si] & 1, tf & 1)
+            for r in numpy.nonzero(tf & 1)[0]:
+                n_rows += 1
+                if (flags[si][r] & 2) != (tf[r] & 2):
+                    n_diff += 1
+                    assert abs(mg[r] + 1e-9) < 2e-8, (name, a, int(r), float(mg[r]))
+    assert n_diff <= 0.01 * n_rows
+    eng.close()
