@@ -5,8 +5,8 @@
 // mpLP cardinality filter (mpqp_combinatorial.py:40-42).  The reference tests every child against EVERY stored
 // infeasible tuple (linear scan, the measured bottleneck at MPC N=10).  Here a child C = P + {i} of a feasible parent P
 // survives iff every k-subset C \ {j}, j in P, is itself in this level's FEASIBLE list - equivalent to "no subset of C is
-// in the murder list" by induction over levels - and the feasible list is already sorted in the
-// reference's lexicographic order, so each test is a binary search over 8*W-byte keys.
+// in the murder list" by induction over levels; the feasible masks of the level go into an
+// open-addressing hash set (load <= 0.5), so each test is ~1.5 probes instead of a 22-step binary search.
 // Children are written parent by parent in ascending i, i.e. in the reference's order.
 #include "common.cuh"
 #include "launch.h"
@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const long lon
 
 size_t scan_workspace_bytes(long long n) {
     const long long nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 1;
-    return (size_t)(n + 1 + nb + 2) * sizeof(long long);  // offsets, block sums (+ total), one result slot
+    // offsets, block sums (+ total), one result slot, and (K6) an open-addressing table of up to 4n int32 slots
+    const long long table = 2 * n + 2 > 1024 ? 2 * n + 2 : 1024;  // >= 2048 int32 slots even for tiny levels
+    return (size_t)(n + 1 + nb + 2 + table) * sizeof(long long);
 }
 
 // exclusive scan of vals[0..n) in place -> vals[0..n], vals[n] = total; bsum = scratch of nb+1
@@ -128,7 +130,7 @@ __global__ void select_scatter_kernel(const uint8_t* __restrict__ status, long l
 // ordered compaction: indices i with (status[i] & bits) == value, ascending; *d_count = how many
 cudaError_t select_indices(const uint8_t* status, long long n, uint8_t bits, uint8_t value, long long* idx_out,
                            long long* d_count, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (ws_bytes + sizeof(long long) < scan_workspace_bytes(n)) return cudaErrorInvalidValue;
+    if (ws_bytes + sizeof(long long) < (size_t)(n + 1 + (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 3) * sizeof(long long)) return cudaErrorInvalidValue;
     long long* offs = (long long*)ws;
     long long* bsum = offs + n + 1;
     if (n == 0) return cudaMemsetAsync(d_count, 0, sizeof(long long), st);
@@ -193,20 +195,44 @@ __device__ __forceinline__ int lex_cmp4(const uint64_t* __restrict__ a, const Ma
     return res;
 }
 
-__device__ __forceinline__ bool sorted_contains(const uint64_t* __restrict__ keys, long long nk, int W, const Mask4& key) {
-    long long lo = 0, hi = nk;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        const int c = lex_cmp4(keys + mid * W, key, W);
-        if (c == 0) return true;
-        if (c < 0) lo = mid + 1; else hi = mid;
+__device__ __forceinline__ unsigned hash_mask(const Mask4& k, int W) {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+    for (int x = 0; x < MAXW; ++x)
+        if (x < W) { h ^= k.w[x]; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
+    return (unsigned)h;
+}
+
+// open-addressing set of this level's feasible masks: table slots hold an index into `feas` (-1 = empty)
+__global__ void hash_insert_kernel(const uint64_t* __restrict__ feas, long long nf, int W, int* __restrict__ table, unsigned cap_mask) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nf) return;
+    Mask4 k;
+#pragma unroll
+    for (int x = 0; x < MAXW; ++x) k.w[x] = x < W ? feas[p * W + x] : 0ull;
+    unsigned slot = hash_mask(k, W) & cap_mask;
+    while (atomicCAS(&table[slot], -1, (int)p) != -1) slot = (slot + 1) & cap_mask;
+}
+
+__device__ __forceinline__ bool hash_contains(const uint64_t* __restrict__ feas, int W, const int* __restrict__ table,
+                                              unsigned cap_mask, const Mask4& key) {
+    unsigned slot = hash_mask(key, W) & cap_mask;
+    for (;;) {
+        const int e = __ldg(table + slot);
+        if (e < 0) return false;
+        bool same = true;
+#pragma unroll
+        for (int x = 0; x < MAXW; ++x)
+            if (x < W && feas[(long long)e * W + x] != key.w[x]) same = false;
+        if (same) return true;
+        slot = (slot + 1) & cap_mask;
     }
-    return false;
 }
 
 __global__ void __launch_bounds__(128)
 children_count_kernel(DevProgram P, const uint64_t* __restrict__ feas, long long nf, int k_act, uint64_t* __restrict__ survive,
-                      long long* __restrict__ counts, unsigned long long* __restrict__ counters) {
+                      long long* __restrict__ counts, unsigned long long* __restrict__ counters,
+                      const int* __restrict__ table, unsigned cap_mask) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -249,7 +275,7 @@ children_count_kernel(DevProgram P, const uint64_t* __restrict__ feas, long long
 #pragma unroll
                                 for (int x = 0; x < MAXW; ++x) sub.w[x] = child.w[x] & ~((x == w) ? (1ull << b) : 0ull);
                                 ++lookups;
-                                if (!sorted_contains(feas, nf, W, sub)) ok = false;
+                                if (!hash_contains(feas, W, table, cap_mask, sub)) ok = false;
                             }
                         }
                     }
@@ -299,12 +325,19 @@ cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const lon
     if (P.W > MAXW) return cudaErrorInvalidValue;
     if (nf == 0) return cudaMemsetAsync(offsets, 0, sizeof(long long), st);
     const long long nb = (nf + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    if (ws_bytes < (size_t)(nb + 2) * sizeof(long long)) return cudaErrorInvalidValue;
+    if (nf >= (1ll << 30)) return cudaErrorInvalidValue;
+    unsigned cap = 1024;
+    while ((long long)cap < 2 * nf) cap <<= 1;          // load factor in (0.25, 0.5]
+    if (ws_bytes < (size_t)(nb + 2) * sizeof(long long) + (size_t)cap * sizeof(int)) return cudaErrorInvalidValue;
+    int* table = reinterpret_cast<int*>((long long*)ws + nb + 2);
     const long long ne = nf * P.W;
     gather_masks_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(masks, feas_idx, nf, P.W, feas_masks);
+    cudaError_t e = cudaMemsetAsync(table, 0xff, (size_t)cap * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    hash_insert_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(feas_masks, nf, P.W, table, cap - 1);
     long long blocks = (nf * 32 + 127) / 128;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    children_count_kernel<<<(unsigned)blocks, 128, 0, st>>>(P, feas_masks, nf, k_act, survive, offsets, counters);
+    children_count_kernel<<<(unsigned)blocks, 128, 0, st>>>(P, feas_masks, nf, k_act, survive, offsets, counters, table, cap - 1);
     return scan_inplace(offsets, nf, (long long*)ws, st);
 }
 
