@@ -1,10 +1,9 @@
-"""Program containers with the attribute surface the combinatorial path reads from the reference's
-MPLP_Program / MPQP_Program (/root/reference/src/ppopt/mplp_program.py:45-58,140-156; mpqp_program.py:15-42).
+"""Program containers with the constructor signature and attribute surface of the reference's MPLP_Program /
+MPQP_Program (/root/reference/src/ppopt/mplp_program.py:45-134,140-156; mpqp_program.py:15-42).
 
-Round-1 scope: these hold ALREADY PRESOLVED data (the arrays a reference program object has after its constructor ran:
-equalities first and renumbered 0..n_eq-1, theta-only rows moved to A_t, rows of [A|-F] L2-normalised, redundant rows
-removed).  The reference's presolve itself (process_constraints etc., one LP per row) is SURVEY.md section 8f row 1 and
-is not re-implemented yet; genuine ppopt program objects can be passed to the engine directly instead.
+``MPQP_Program(A, b, c, H, Q, A_t, b_t, F, equality_indices=..., post_process=True)`` runs the reference's presolve
+(presolve.py: host numpy steps + one GPU batch of redundancy LPs).  ``presolved=True`` skips all processing for data that
+already went through a program constructor (tests/golden fixtures, genuine ppopt objects' arrays).
 """
 from typing import List, Optional
 
@@ -22,12 +21,15 @@ class MPLP_Program:
     r"""min theta'H'x + c'x  s.t.  A x <= b + F theta (first n_eq rows equalities),  A_t theta <= b_t."""
 
     def __init__(self, A, b, c, H, A_t, b_t, F, c_c=None, c_t=None, Q_t=None, equality_indices=None, solver=None,
-                 post_process=False):
-        if post_process:
-            raise NotImplementedError('presolve is not part of the round-1 scope: pass presolved arrays '
-                                      '(post_process=False) or a ppopt program object')
+                 post_process=True, presolved=False):
         self.A, self.b, self.c, self.H = _f64(A), _f64(b), _f64(c), _f64(H)
         self.A_t, self.b_t, self.F = _f64(A_t), _f64(b_t), _f64(F)
+        if not presolved:
+            from . import presolve
+            self.A, self.b, self.F, self.A_t, self.b_t, equality_indices = presolve.base_processing(
+                self.A, self.b, self.F, self.A_t, self.b_t, [] if equality_indices is None else list(equality_indices))
+            if post_process and type(self) is MPLP_Program:
+                self.process_constraints(len(equality_indices))
         t = self.F.shape[1]
         self.c_c = numpy.array([[0.0]]) if c_c is None else _f64(c_c)
         self.c_t = numpy.zeros((t, 1)) if c_t is None else _f64(c_t)
@@ -37,6 +39,13 @@ class MPLP_Program:
             raise ValueError('presolved programs have their equality rows first: equality_indices must be range(n_eq)')
         self.equality_indices: List[int] = eq
         self.solver = solver
+
+    def process_constraints(self, n_eq=None) -> None:
+        """Removes redundant constraints (mplp_program.py:285-306); the per-row LPs run as one GPU batch."""
+        from . import presolve
+        n_eq = len(self.equality_indices) if n_eq is None else n_eq
+        self.A, self.b, self.F, self.A_t, self.b_t = [numpy.ascontiguousarray(x) for x in presolve.remove_redundant(
+            self.A, self.b, self.F, self.A_t, self.b_t, n_eq)]
 
     def num_x(self) -> int:
         return self.A.shape[1]
@@ -63,9 +72,12 @@ class MPQP_Program(MPLP_Program):
     r"""min 1/2 x'Qx + theta'H'x + c'x  with the constraints of MPLP_Program."""
 
     def __init__(self, A, b, c, H, Q, A_t, b_t, F, c_c=None, c_t=None, Q_t=None, equality_indices=None, solver=None,
-                 post_process=False):
+                 post_process=True, presolved=False):
         self.Q = _f64(Q)
-        super().__init__(A, b, c, H, A_t, b_t, F, c_c, c_t, Q_t, equality_indices, solver, post_process)
+        super().__init__(A, b, c, H, A_t, b_t, F, c_c, c_t, Q_t, equality_indices, solver, post_process=False,
+                         presolved=presolved)
+        if post_process and not presolved:  # same order as the reference: base processing first, then redundancy
+            self.process_constraints()
 
     def evaluate_objective(self, x, theta_point) -> float:
         v = 0.5 * x.T @ self.Q @ x + theta_point.T @ self.H.T @ x + self.c.T @ x + self.c_c \
@@ -78,5 +90,6 @@ def load_presolved(path: str):
     g = numpy.load(path)
     eq = list(range(int(g['n_eq'])))
     if str(g['kind']) == 'qp':
-        return MPQP_Program(g['A'], g['b'], g['c'], g['H'], g['Q'], g['A_t'], g['b_t'], g['F'], equality_indices=eq)
-    return MPLP_Program(g['A'], g['b'], g['c'], g['H'], g['A_t'], g['b_t'], g['F'], equality_indices=eq)
+        return MPQP_Program(g['A'], g['b'], g['c'], g['H'], g['Q'], g['A_t'], g['b_t'], g['F'], equality_indices=eq,
+                            presolved=True)
+    return MPLP_Program(g['A'], g['b'], g['c'], g['H'], g['A_t'], g['b_t'], g['F'], equality_indices=eq, presolved=True)

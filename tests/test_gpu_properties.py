@@ -217,3 +217,30 @@ def test_redundancy_flags_match_cpu_checker(name):
                     assert abs(mg[r] + 1e-9) < 2e-8, (name, a, int(r), float(mg[r]))
     assert n_diff <= 0.01 * n_rows
     eng.close()
+
+
+def test_constructor_presolve_matches_reference():
+    """MPQP_Program / MPLP_Program built from RAW data (constructor presolve, redundancy LPs batched on
+    the GPU) must end with exactly the arrays the reference constructor produced, for every golden program"""
+    from conftest import golden_names
+    from ppopt_b200 import MPLP_Program, MPQP_Program
+    for name in golden_names():
+        g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
+        kw = dict(equality_indices=g['raw_equality_indices'].tolist(), post_process=bool(g['raw_post_process']))
+        if str(g['kind']) == 'qp':
+            p = MPQP_Program(g['raw_A'], g['raw_b'], g['raw_c'], g['raw_H'], g['raw_Q'], g['raw_A_t'], g['raw_b_t'], g['raw_F'], **kw)
+        else:
+            p = MPLP_Program(g['raw_A'], g['raw_b'], g['raw_c'], g['raw_H'], g['raw_A_t'], g['raw_b_t'], g['raw_F'], **kw)
+        assert len(p.equality_indices) == int(g['n_eq']), name
+        for fld in ('A', 'b', 'F', 'A_t', 'b_t'):
+            assert numpy.array_equal(getattr(p, fld), g[fld]), (name, fld, getattr(p, fld).shape, g[fld].shape)
+
+
+def test_raw_to_solution_end_to_end():
+    """raw data -> constructor presolve -> solve_mpqp: the whole user path without any reference code"""
+    from ppopt_b200 import MPQP_Program, mpqp_algorithm, problems, solve_mpqp
+    d = problems.mpc_double_integrator(5)
+    prog = MPQP_Program(d['A'], d['b'], d['c'], d['H'], d['Q'], d['A_t'], d['b_t'], d['F'], equality_indices=d['equality_indices'])
+    sol = solve_mpqp(prog, mpqp_algorithm.combinatorial)
+    g = numpy.load(os.path.join(GOLDEN, 'mpc_n5.npz'))
+    assert [list(r.active_set) for r in sol.critical_regions] == [g[f'r{i}_active_set'].tolist() for i in range(int(g['n_regions']))]

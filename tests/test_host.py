@@ -80,7 +80,7 @@ def test_program_arrays_validation():
     with pytest.raises(ValueError):
         engine.program_arrays(p)
     with pytest.raises(ValueError):
-        MPQP_Program(p.A, p.b, p.c, numpy.zeros((4, 2)), p.Q, p.A_t, p.b_t, p.F, equality_indices=[1])
+        MPQP_Program(p.A, p.b, p.c, numpy.zeros((4, 2)), p.Q, p.A_t, p.b_t, p.F, equality_indices=[1], presolved=True)
     lp = load_presolved(os.path.join(GOLDEN, 'transport_mplp.npz'))
     assert not engine.program_arrays(lp)['is_qp']
 
@@ -145,3 +145,32 @@ def test_level_sharding_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def _is_ordered_subset(sub, full):
+    j = 0
+    for r in sub:
+        while j < full.shape[0] and not numpy.array_equal(full[j], r):
+            j += 1
+        if j == full.shape[0]:
+            return False
+        j += 1
+    return True
+
+
+def test_presolve_host_steps_reproduce_reference_arrays():
+    """base processing (equalities first, parametric rows moved, L2 scaling, implicit / dependent equalities) must give
+    bit-identical rows to the reference constructor; redundancy removal (GPU) can only delete rows, so the golden rows
+    must appear, in order and bitwise, among the base-processed ones"""
+    from conftest import golden_names
+    from ppopt_b200 import presolve
+    for name in golden_names():
+        g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
+        A, b, F, A_t, b_t, eq = presolve.base_processing(g['raw_A'], g['raw_b'], g['raw_F'], g['raw_A_t'], g['raw_b_t'],
+                                                         g['raw_equality_indices'].tolist())
+        assert eq == list(range(int(g['n_eq']))), name
+        main = numpy.hstack([A, b, F])
+        assert _is_ordered_subset(numpy.hstack([g['A'], g['b'], g['F']]), main), name
+        assert _is_ordered_subset(numpy.hstack([g['A_t'], g['b_t']]), numpy.hstack([A_t, b_t])), name
+        if not bool(g['raw_post_process']):
+            assert numpy.array_equal(main, numpy.hstack([g['A'], g['b'], g['F']]))
