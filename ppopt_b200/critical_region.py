@@ -1,51 +1,44 @@
-"""Result container with the fields of the reference's CriticalRegion
-(/root/reference/src/ppopt/critical_region.py:9-48).  Used only when PPOPT itself is not importable; when the solved
-program is a genuine ppopt object the engine returns ppopt's own class (see mp_solvers/mpqp_combinatorial.py)."""
-from dataclasses import dataclass, field
-from typing import List, Optional
+"""Region record returned by the engine when PPOPT itself is not importable.
 
+Field names and meaning follow the reference's result type (/root/reference/src/ppopt/critical_region.py:9-48) so that
+code written against PPOPT reads the same attributes; when the solved program is a genuine ppopt object the engine
+returns ppopt's own class instead (engine._region_classes)."""
 import numpy
 
 
-@dataclass(eq=False)
 class CriticalRegion:
-    r"""x(theta) = A theta + b,  lambda(theta) = C theta + d,  region = {theta : E theta <= f}."""
-    A: numpy.ndarray
-    b: numpy.ndarray
-    C: numpy.ndarray
-    d: numpy.ndarray
-    E: numpy.ndarray
-    f: numpy.ndarray
-    active_set: List[int]
+    """x*(theta) = A theta + b, lambda*(theta) = C theta + d on the polytope {theta : E theta <= f}."""
 
-    omega_set: List[int] = field(default_factory=list)
-    lambda_set: List[int] = field(default_factory=list)
-    regular_set: List[List[int]] = field(default_factory=list)
+    __slots__ = ('A', 'b', 'C', 'd', 'E', 'f', 'active_set', 'omega_set', 'lambda_set', 'regular_set', 'y_fixation',
+                 'y_indices', 'x_indices')
 
-    y_fixation: Optional[numpy.ndarray] = None
-    y_indices: Optional[numpy.ndarray] = None
-    x_indices: Optional[numpy.ndarray] = None
+    def __init__(self, A, b, C, d, E, f, active_set, omega_set=None, lambda_set=None, regular_set=None, y_fixation=None,
+                 y_indices=None, x_indices=None):
+        self.A, self.b, self.C, self.d, self.E, self.f = A, b, C, d, E, f
+        self.active_set = active_set
+        self.omega_set = [] if omega_set is None else omega_set        # kept Theta rows
+        self.lambda_set = [] if lambda_set is None else lambda_set     # constraints whose lambda >= 0 facet was kept
+        self.regular_set = [] if regular_set is None else regular_set  # [positions, constraint indices] of kept inactive rows
+        self.y_fixation, self.y_indices, self.x_indices = y_fixation, y_indices, x_indices
 
     def __repr__(self):
-        return (f"Critical region with active set {self.active_set}\nThe Omega Constraint indices are {self.omega_set}"
-                f"\nThe Lagrange multipliers Constraint indices are {self.lambda_set}"
-                f"\nThe Regular Constraint indices are {self.regular_set}"
-                f"\n A = {self.A} \n b = {self.b} \n C = {self.C} \n d = {self.d} \n E = {self.E} \n f = {self.f}")
+        return (f'CriticalRegion(active_set={self.active_set}, omega={self.omega_set}, lambda={self.lambda_set}, '
+                f'regular={self.regular_set}, E{numpy.shape(self.E)}, A{numpy.shape(self.A)})')
 
-    def evaluate(self, theta: numpy.ndarray) -> numpy.ndarray:
+    def evaluate(self, theta):
+        x = self.A @ theta + self.b
         if self.y_fixation is None:
-            return self.A @ theta + self.b
-        cont = self.A @ theta + self.b
-        x_star = numpy.zeros((len(self.x_indices) + len(self.y_indices),))
-        x_star[self.x_indices] = cont.flatten()
-        x_star[self.y_indices] = self.y_fixation
-        return x_star.reshape(-1, 1)
+            return x
+        full = numpy.zeros(len(self.x_indices) + len(self.y_indices))
+        full[self.x_indices] = x.ravel()
+        full[self.y_indices] = self.y_fixation
+        return full.reshape(-1, 1)
 
-    def lagrange_multipliers(self, theta: numpy.ndarray) -> numpy.ndarray:
+    def lagrange_multipliers(self, theta):
         return self.C @ theta + self.d
 
-    def is_inside(self, theta: numpy.ndarray, tol: float = 1e-5) -> bool:
-        return bool(numpy.all(self.E @ theta - self.f < tol))
+    def is_inside(self, theta, tol=1e-5) -> bool:
+        return bool((self.E @ theta - self.f < tol).all())
 
     def get_constraints(self):
         return [self.E, self.f]

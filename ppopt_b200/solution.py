@@ -1,45 +1,38 @@
-"""Solution container with the surface of the reference's Solution (/root/reference/src/ppopt/solution.py:15-112)."""
-from typing import List, Optional
-
-import numpy
-
-from .critical_region import CriticalRegion
+"""Solution record with the surface of the reference's Solution (/root/reference/src/ppopt/solution.py:15-112): the
+solved program, the ordered list of critical regions, and first-hit / best-objective point location."""
 
 
 class Solution:
-    def __init__(self, program, critical_regions: List[CriticalRegion], is_overlapping=False,
-                 point_location_tolerance=1e-5):
+    def __init__(self, program, critical_regions, is_overlapping=False, point_location_tolerance=1e-5):
         self.program = program
         self.critical_regions = critical_regions
         self.is_overlapping = is_overlapping
         self.point_location_tolerance = point_location_tolerance
 
-    def add_region(self, region: CriticalRegion) -> None:
+    def add_region(self, region):
         self.critical_regions.append(region)
-
-    def evaluate(self, theta_point: numpy.ndarray) -> Optional[numpy.ndarray]:
-        cr = self.get_region(theta_point)
-        return None if cr is None else cr.evaluate(theta_point)
-
-    def get_region(self, theta_point: numpy.ndarray) -> Optional[CriticalRegion]:
-        if self.is_overlapping:
-            return self.get_region_overlap(theta_point)
-        return self.get_region_no_overlap(theta_point)
-
-    def get_region_no_overlap(self, theta_point):
-        for region in self.critical_regions:
-            if region.is_inside(theta_point, self.point_location_tolerance):
-                return region
-        return None
-
-    def get_region_overlap(self, theta_point):
-        best, best_obj = None, float('inf')
-        for region in self.critical_regions:
-            if region.is_inside(theta_point, self.point_location_tolerance):
-                obj = self.program.evaluate_objective(region.evaluate(theta_point), theta_point)
-                if obj <= best_obj:
-                    best, best_obj = region, obj
-        return best
 
     def __len__(self):
         return len(self.critical_regions)
+
+    def _containing(self, theta):
+        tol = self.point_location_tolerance
+        return (r for r in self.critical_regions if r.is_inside(theta, tol))
+
+    def get_region_no_overlap(self, theta):
+        return next(self._containing(theta), None)
+
+    def get_region_overlap(self, theta):
+        best, best_val = None, float('inf')
+        for r in self._containing(theta):
+            val = self.program.evaluate_objective(r.evaluate(theta), theta)
+            if val <= best_val:
+                best, best_val = r, val
+        return best
+
+    def get_region(self, theta):
+        return self.get_region_overlap(theta) if self.is_overlapping else self.get_region_no_overlap(theta)
+
+    def evaluate(self, theta):
+        r = self.get_region(theta)
+        return None if r is None else r.evaluate(theta)
