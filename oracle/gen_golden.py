@@ -62,6 +62,7 @@ PLAN = {
     'rand_5_3_10_s2': (None, True),
     'rand_lp_4_2_8_s3': (None, True),
     'synthetic_30_6_40_s0': (2, False),
+    'rand_wide_40_8_90_s5': (2, False),
 }
 
 

@@ -212,4 +212,6 @@ CONFIGS = {
     'rand_5_3_10_s2': lambda: random_mpqp(5, 3, 10, 2),
     'rand_lp_4_2_8_s3': lambda: random_mpqp(4, 2, 8, 3, kind='lp'),
     'synthetic_30_6_40_s0': lambda: random_mpqp(30, 6, 40, 0),
+    # exercises the wide template instantiations: n' > 32, t > 6, more than 128 rows
+    'rand_wide_40_8_90_s5': lambda: random_mpqp(40, 8, 90, 5),
 }

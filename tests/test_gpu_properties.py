@@ -244,3 +244,29 @@ def test_raw_to_solution_end_to_end():
     sol = solve_mpqp(prog, mpqp_algorithm.combinatorial)
     g = numpy.load(os.path.join(GOLDEN, 'mpc_n5.npz'))
     assert [list(r.active_set) for r in sol.critical_regions] == [g[f'r{i}_active_set'].tolist() for i in range(int(g['n_regions']))]
+
+
+def test_wide_templates_emission_matches_cpu_checker():
+    """rand_wide_40_8_90_s5 (n'=40 > 32, t=8 > 6, 186 rows > 128) drives the widest kernel instantiations (K1 NP=64, K2
+    8 warps x 64 columns, K3/K4/K5 8 rows per lane x 16 columns).  No region exists at levels 1-2, so K5 is checked on
+    arbitrary feasible candidates: laws and normalised rows against the CPU checker."""
+    import torch
+    import twin_binding
+    engine, prog, eng = _engine('rand_wide_40_8_90_s5')
+    path = os.path.join(GOLDEN, 'rand_wide_40_8_90_s5.npz')
+    g = numpy.load(path)
+    tw = twin_binding.Twin.from_npz(path)
+    cands, st = g['level1_candidates'], g['level1_status']
+    pick = numpy.nonzero(st & 2)[0][::701][:16]
+    asets = [cands[i].tolist() for i in pick]
+    masks = eng.masks_from_lists(asets)
+    status = torch.full((len(asets),), 7, dtype=torch.uint8, device=eng.tdev)
+    sel = torch.arange(len(asets), dtype=torch.int64, device=eng.tdev)
+    laws, rows, flags, info = [x.cpu().numpy() for x in eng.emit(masks, sel, 2, status)]
+    for si, a in enumerate(asets):
+        rc, tl, tr, tf, ti = tw.emit(tw.masks([a])[0])
+        assert (info[si, 0] == 1.0) == (rc == 1)
+        assert numpy.allclose(laws[si], tl, rtol=1e-8, atol=1e-8 * max(1.0, numpy.abs(tl).max()))
+        assert numpy.array_equal(flags[si] & 1, tf & 1)
+        assert numpy.allclose(rows[si], tr, rtol=1e-8, atol=1e-8 * max(1.0, numpy.abs(tr).max()))
+    eng.close()
