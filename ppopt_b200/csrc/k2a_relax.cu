@@ -135,6 +135,7 @@ k2a_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
             isA[rr] = r < P.mi && mask_test(mk, r);
         }
         exact_residuals();
+        __syncwarp();  // zs is rewritten by the first re-verification
         bool feasible = false;
         int rechecks = 0;
         for (int it = 0; it < max_iter; ++it) {
@@ -150,6 +151,7 @@ k2a_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                 for (int cc = 0; cc < 2; ++cc) if (cc * 32 + lane < nf) zs[cc * 32 + lane] = z[cc];
                 __syncwarp();
                 exact_residuals();
+                __syncwarp();  // zs is rewritten by a later re-verification
                 double worst = 0.0;
 #pragma unroll
                 for (int rr = 0; rr < RPL; ++rr)
@@ -198,6 +200,7 @@ k2a_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                     z[cc] = fma(-tau, d, z[cc]);
                 }
             }
+            __syncwarp();  // ga / wv are rewritten by the next step
         }
         if (feasible) {
             ++n_ok;
@@ -464,6 +467,7 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                 for (int b2 = 0; b2 < KC; ++b2) wa = fma(srow[b2], g2[b2], wa);
                 if (lane < k) cA = fma(tau, wa, cA);
             }
+            __syncwarp();  // lane 0's update of cs / touched must be visible to the next step's broadcast read
         }
         if (feasible) {
             ++n_ok;

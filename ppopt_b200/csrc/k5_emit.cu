@@ -31,7 +31,8 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
     __shared__ double red_v[K5_WARPS];
     __shared__ int red_i[K5_WARPS];
     __shared__ double s_info[4];
-    __shared__ int s_ok;
+    __shared__ int s_ok;    // KKT solved and no zero row with negative rhs
+    __shared__ int s_full;  // full-dimension test passed
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = P.n, t = P.t, t1 = P.t + 1, m = P.m, ne = P.ne, mi = P.mi, R0 = P.R0, W = P.W;
     const int k = ne + k_act, N = n + k, ld = N + t1;
@@ -39,6 +40,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
     double* rows = M + (size_t)N * ld;                     // R0 x t1
     int* flags = reinterpret_cast<int*>(rows + (size_t)R0 * t1);  // R0
     int* actf = flags + R0;                                // k
+    int* keptf = actf + k;                                 // R0: redundancy verdicts (merged into flags after a barrier)
     unsigned long long n_lp = 0, n_piv = 0, n_work = 0;
 
     for (long long si = blockIdx.x; si < n_sel; si += gridDim.x) {
@@ -46,7 +48,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
         const uint64_t* mk = masks + idx * W;
         __syncthreads();
         for (int j = tid; j < k; j += K5_THREADS) actf[j] = j < ne ? j : ne + mask_nth(mk, W, j - ne);
-        if (tid == 0) { s_ok = 1; s_info[0] = 0.0; s_info[1] = -CUDART_INF; s_info[2] = -CUDART_INF; s_info[3] = CUDART_INF; }
+        if (tid == 0) { s_ok = 1; s_full = 0; s_info[0] = 0.0; s_info[1] = -CUDART_INF; s_info[2] = -CUDART_INF; s_info[3] = CUDART_INF; }
         __syncthreads();
         // ---- KKT matrix
         for (int e = tid; e < N * ld; e += K5_THREADS) {
@@ -168,9 +170,10 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
 #pragma unroll
                         for (int c = 0; c < DC; ++c) v[c] *= inv;
                     } else if (v[0] < -PPG_FEAS_TOL) {
-                        s_ok = 0;  // zero row with negative rhs: not optimal (benign race: every writer stores 0)
+                        atomicExch(&s_ok, 0);  // zero row with negative rhs: not optimal
                     }
                     flags[r] = fl;
+                    keptf[r] = 0;
 #pragma unroll
                     for (int c = 0; c < DC; ++c)
                         if (c < t1) rows[(size_t)r * t1 + c] = v[c];
@@ -196,7 +199,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
                     }
                     if (lane == 0) {
                         s_info[1] = 0.5 * (hi - lo); s_info[2] = lo; s_info[3] = hi;
-                        s_ok = (lo + PPG_WIDTH_1D <= hi) ? 1 : 0;
+                        s_full = (lo + PPG_WIDTH_1D <= hi) ? 1 : 0;
                     }
                 } else {
                     double T[RPT][DC];
@@ -212,11 +215,11 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
                     LpOut res = Core::solve(sh_all[0], T, rflag, R0, t1, PPG_RADIUS, true, lane);
                     n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
                     const bool ok = res.code == PPG_LP_EARLY || (res.code == PPG_LP_OPTIMAL && res.beta > PPG_RADIUS);
-                    if (lane == 0) { s_info[1] = res.beta; s_ok = ok ? 1 : 0; }
+                    if (lane == 0) { s_info[1] = res.beta; s_full = ok ? 1 : 0; }
                 }
             }
             __syncthreads();
-            region = s_ok != 0;
+            region = s_full != 0;
         }
         // ---- redundancy tests
         if (region) {
@@ -225,7 +228,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
                 for (int r = tid; r < R0; r += K5_THREADS)
                     if (flags[r] & 1) {
                         const double q = rows[(size_t)r * 2] / rows[(size_t)r * 2 + 1];
-                        if (lo <= q && q <= hi) flags[r] |= 2;
+                        if (lo <= q && q <= hi) keptf[r] = 1;
                     }
             } else {
                 for (int a = warp; a < R0; a += K5_WARPS) {
@@ -245,23 +248,28 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
                     n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
                     const bool feas = res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED ||
                                       (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_REDUND_TOL);
-                    if (lane == 0 && feas) atomicOr(&flags[a], 2);
+                    if (lane == 0 && feas) keptf[a] = 1;
                 }
             }
             __syncthreads();
+            for (int r = tid; r < R0; r += K5_THREADS) if (keptf[r]) flags[r] |= 2;
+            __syncthreads();
             if (t != 1) {
-                // duplicates among kept rows (value equality, first occurrence survives)
+                // duplicates among kept rows (value equality, first occurrence survives); verdicts land after a barrier
                 for (int i = tid; i < R0; i += K5_THREADS) {
-                    if ((flags[i] & 3) != 3) continue;
                     bool dup = false;
-                    for (int j = 0; j < i && !dup; ++j) {
-                        if ((flags[j] & 3) != 3) continue;
-                        bool same = true;
-                        for (int c = 0; c < t1 && same; ++c) same = rows[(size_t)i * t1 + c] == rows[(size_t)j * t1 + c];
-                        dup = same;
+                    if ((flags[i] & 3) == 3) {
+                        for (int j = 0; j < i && !dup; ++j) {
+                            if ((flags[j] & 3) != 3) continue;
+                            bool same = true;
+                            for (int c = 0; c < t1 && same; ++c) same = rows[(size_t)i * t1 + c] == rows[(size_t)j * t1 + c];
+                            dup = same;
+                        }
                     }
-                    if (dup) atomicOr(&flags[i], 4);
+                    keptf[i] = dup ? 1 : 0;
                 }
+                __syncthreads();
+                for (int r = tid; r < R0; r += K5_THREADS) if (keptf[r]) flags[r] |= 4;
             }
             __syncthreads();
         }
@@ -292,7 +300,7 @@ static cudaError_t launch_k5_t(const DevProgram& P, const uint64_t* masks, const
                                unsigned long long* counters, int sm_count, cudaStream_t st) {
     auto kern = k5_emit_kernel<RPT, DC>;
     const int k = P.ne + k_act, N = P.n + k, ld = N + P.t + 1;
-    const size_t smem = ((size_t)N * ld + (size_t)P.R0 * (P.t + 1)) * sizeof(double) + (size_t)(P.R0 + k + 2) * sizeof(int);
+    const size_t smem = ((size_t)N * ld + (size_t)P.R0 * (P.t + 1)) * sizeof(double) + (size_t)(2 * P.R0 + k + 2) * sizeof(int);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e;
     if (smem > 48 * 1024) {
