@@ -331,9 +331,9 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
         // padded active slots that point at a valid row but carry M == 0.
         double M[RPL][KC], v[RPL];
         bool isA[RPL], use[RPL];
-        const double* growA[KC];
+        unsigned growA[KC];   // element offsets of the active rows of Gam (32-bit: base pointer stays uniform)
 #pragma unroll
-        for (int a = 0; a < KC; ++a) growA[a] = Gam + (size_t)act[a < k ? a : 0] * R0;
+        for (int a = 0; a < KC; ++a) growA[a] = (unsigned)act[a < k ? a : 0] * (unsigned)R0;
         int rcl[RPL];
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) rcl[rr] = min(rr * 32 + lane, R0 - 1);
@@ -357,7 +357,7 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
                 const int r = rr * 32 + lane;
                 double gA[KC];
 #pragma unroll
-                for (int a = 0; a < KC; ++a) gA[a] = (a < k) ? __ldg(growA[a] + rcl[rr]) : 0.0;
+                for (int a = 0; a < KC; ++a) gA[a] = (a < k) ? __ldg(Gam + (growA[a] + (unsigned)rcl[rr])) : 0.0;
                 double s2 = -__ldg(T0 + (size_t)rcl[rr] * dc0);
 #pragma unroll
                 for (int a = 0; a < KC; ++a) {
@@ -435,13 +435,13 @@ k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long lo
             ++n_it;
             double g2[KC];
 #pragma unroll
-            for (int a = 0; a < KC; ++a) g2[a] = __ldg(growA[a] + irow);  // broadcast loads (padded slots: M == 0)
-            const double* __restrict__ gi = Gam + (size_t)irow * R0;
+            for (int a = 0; a < KC; ++a) g2[a] = __ldg(Gam + (growA[a] + (unsigned)irow));  // broadcast loads (padded slots: M == 0)
+            const unsigned gi = (unsigned)irow * (unsigned)R0;
             double c2[RPL];
             double mycol = 0.0;
 #pragma unroll
             for (int rr = 0; rr < RPL; ++rr) {
-                double x2 = __ldg(gi + rcl[rr]);
+                double x2 = __ldg(Gam + (gi + (unsigned)rcl[rr]));
 #pragma unroll
                 for (int a = 0; a < KC; ++a) x2 = fma(-M[rr][a], g2[a], x2);
                 c2[rr] = x2;
