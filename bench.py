@@ -221,6 +221,8 @@ def run_gpu(args, rank, world, local_rank):
         sampler.join(timeout=2)
     prof = eng.profile_read(reset=True)
     eng.profile(False)
+    if os.environ.get('PPGPU_BENCH_VERBOSE'):
+        print(f'[rank {rank}] ms/step dev {sum(ms_dev) / len(ms_dev):.1f} kernels ' + str({k: round(v['ms'] / len(ms_dev), 1) for k, v in prof.items() if v['launches']}), file=sys.stderr, flush=True)
     counters = eng.counters()
     launches = eng.launch_count() - launches0
     levels_stats = sol.level_stats

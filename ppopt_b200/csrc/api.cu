@@ -58,10 +58,12 @@ static int fail_msg(const std::string& m) { g_err = m; return -2; }
 template <class T>
 static cudaError_t upload(ppgpu_program* p, const std::vector<T>& v, const T** out) {
     void* d = nullptr;
-    const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    // 1 KiB zero tail: K2a reads 32-wide row segments of Gam without clamping the last one (k2a_relax.cu)
+    const size_t bytes = v.size() * sizeof(T) + 1024;
     cudaError_t e = cudaMalloc(&d, bytes);
     if (e != cudaSuccess) return e;
     p->allocs.push_back(d);
+    if ((e = cudaMemset(d, 0, bytes)) != cudaSuccess) return e;
     if (v.size()) e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     *out = (const T*)d;
     return e;

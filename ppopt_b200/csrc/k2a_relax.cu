@@ -18,6 +18,8 @@
 #include "launch.h"
 #include "lp_core.cuh"
 
+#include <cstdlib>
+
 namespace ppgpu {
 
 __device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }  // no NaN fix-up (fmax costs ~10 SASS)
@@ -501,6 +503,297 @@ static cudaError_t launch_k2a_small(const DevProgram& P, const uint64_t* masks, 
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2 of the register-cached variant: everything candidate-specific lives in registers.
+//   * Gam[A,A] is factorised as L D L' by every lane redundantly (k' <= 8: ~60 FMAs, no shared memory, no __syncwarp,
+//     no sqrt and k' reciprocals instead of 3k' divisions), M's rows are triangular solves against it;
+//   * the point is carried as the log of its steps (tau_e, row i_e): z = -sum_e tau_e g_{i_e} + G_A' x - one shared
+//     memory store per step, no read;
+//   * arg-max of the violations in ONE 32-bit reduction: key = high word of the violation with the row index in its 7
+//     lowest bits (13 mantissa bits are plenty for a number that only steers the relaxation);
+//   * the exact verification stays in Gram space: residual_r = sum_j c_j Gam[j,r] + sum_a x_a Gam[A_a,r] - h_r with
+//     x = S^-1 (h_A - Gam[A,T] c_T) - coalesced row reads of Gam, every row recomputed (not only near-binding ones),
+//     equality residuals included; same acceptance rule, rounding error ~1e-15 like the z-space evaluation.
+// Rows r >= R0 of a lane are parked at -1e300 and read past the end of a Gam row (the program arrays carry a 1 KiB
+// zero tail, api.cu upload()), which keeps the hot loop free of clamps and bounds predicates.
+template <int KC>
+__device__ __forceinline__ void ldl_solve(const double (&L)[KC][KC], const double (&dinv)[KC], double (&x)[KC]) {
+#pragma unroll
+    for (int i = 1; i < KC; ++i) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c) if (c < i) x[i] = fma(-L[i][c], x[c], x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < KC; ++i) x[i] *= dinv[i];
+#pragma unroll
+    for (int i = KC - 2; i >= 0; --i) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c) if (c > i) x[i] = fma(-L[c][i], x[c], x[i]);
+    }
+}
+
+__device__ __forceinline__ double k2a_key(double v, int idx) {
+    return __hiloint2double(__double2hiint(v), (__double2loint(v) & ~127) | idx);
+}
+
+constexpr int K2A_LOG = 128;  // step log entries per warp (max_iter is clamped to it)
+
+template <int RPL, int KC, bool EXACT>
+__global__ void __launch_bounds__(128, (RPL * KC <= 16) ? 5 : ((RPL * KC <= 24) ? 4 : 3))
+k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
+                     unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter) {
+    constexpr int NL = KC * (KC - 1) / 2;
+    __shared__ double fac_s[4][NL + KC];   // per warp: strict lower triangle of L (row-major), then 1/d
+    __shared__ double log_s[4][K2A_LOG];   // per warp: tau of every step, stepped row in the 7 low mantissa bits
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R0 = P.R0, dc0 = P.dc0, W = P.W, k = EXACT ? KC : k_act;
+    double* fac = fac_s[warp];
+    double* lg = log_s[warp];
+    unsigned lg_sa = (unsigned)__cvta_generic_to_shared(lg);
+    asm volatile("" : "+r"(lg_sa));
+    const double* __restrict__ Gam = P.Gam;
+    const double* __restrict__ T0 = P.T0;
+    if (max_iter > K2A_LOG) max_iter = K2A_LOG;
+    // a key <= ktol proves violation < PPG_FEAS_TOL (keys round down by < 2^-13 relative): time for the exact verification
+    const int ktol = (__double2hiint(PPG_FEAS_TOL * 0.999) & ~127) | 127;
+    // opaque per-lane constants (kept in registers instead of being rematerialised inside the step loop)
+    unsigned long long glane = (unsigned long long)(Gam + lane);
+    asm volatile("" : "+l"(glane));
+    int kid[RPL];
+#pragma unroll
+    for (int rr = 0; rr < RPL; ++rr) { kid[rr] = rr * 32 + lane; asm volatile("" : "+r"(kid[rr])); }
+    unsigned long long n_try = 0, n_ok = 0, n_it = 0;
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(queue, 1ull);
+        const long long idx = (long long)__shfl_sync(PPG_FULL, q, 0);
+        if (idx >= n) break;
+        const uint8_t st = status[idx];
+        if (!(st & PPG_ST_RANK) || (st & PPG_ST_FEAS)) continue;
+        const uint64_t* mk = masks + idx * W;
+        ++n_try;
+        // ---- active rows: lane a < k finds the a-th set bit, everybody gets all of them (padded slots repeat row 0)
+        const int act_lane = mask_nth(mk, W, lane < k ? lane : 0);
+        int act[KC];
+        unsigned long long gp[KC];   // address of Gam[act[a], 0]
+#pragma unroll
+        for (int a = 0; a < KC; ++a) {
+            act[a] = __shfl_sync(PPG_FULL, act_lane, (EXACT || a < k) ? a : 0);
+            gp[a] = (unsigned long long)(Gam + (size_t)act[a] * R0);
+            asm volatile("" : "+l"(gp[a]));
+        }
+#define K2A_GP(a, off) __ldg(reinterpret_cast<const double*>(gp[a]) + (off))
+        // ---- S = Gam[A,A] = L D L' (unit lower L), computed redundantly by every lane; padded slots form an identity block
+        double L[KC][KC], dinv[KC];
+        bool pd = true;
+        {
+            double dd[KC];
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+#pragma unroll
+                for (int j = 0; j < KC; ++j) {
+                    if (j <= i) {
+                        const double e = (EXACT || (i < k && j < k)) ? K2A_GP(i, act[j]) : (i == j ? 1.0 : 0.0);
+                        if (j == i) dd[i] = e; else L[i][j] = e;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < KC; ++j) {
+                double wj[KC];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) if (c < j) { wj[c] = L[j][c] * dd[c]; dd[j] = fma(-L[j][c], wj[c], dd[j]); }
+                pd = pd && (dd[j] > 1e-300);
+                dinv[j] = 1.0 / dd[j];
+#pragma unroll
+                for (int i = 0; i < KC; ++i) {
+                    if (i > j) {
+                        double e = L[i][j];
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) if (c < j) e = fma(-L[i][c], wj[c], e);
+                        L[i][j] = e * dinv[j];
+                    }
+                }
+            }
+        }
+        if (!pd) continue;  // uniform: every lane computed the same factorisation
+        __syncwarp();       // the previous candidate's verification may still be reading fac
+        if (lane == 0) {
+            int o = 0;
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+#pragma unroll
+                for (int j = 0; j < KC; ++j) if (j < i) fac[o++] = L[i][j];
+            }
+#pragma unroll
+            for (int i = 0; i < KC; ++i) fac[NL + i] = dinv[i];
+        }
+        // ---- start point: min-norm solution of the active equalities, z0 = G_A' w0
+        double w0[KC];
+#pragma unroll
+        for (int a = 0; a < KC; ++a) w0[a] = (EXACT || a < k) ? __ldg(T0 + (size_t)act[a] * dc0) : 0.0;
+        ldl_solve<KC>(L, dinv, w0);
+        // ---- per-lane rows: M = Gam[:,A] S^-1 and the start residuals
+        double M[RPL][KC], v[RPL];
+        unsigned amask = 0;  // bit rr: row rr*32+lane is one of the active rows
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int r = rr * 32 + lane;
+            double x[KC];
+#pragma unroll
+            for (int a = 0; a < KC; ++a) x[a] = (EXACT || a < k) ? K2A_GP(a, r) : 0.0;
+            double s2 = -__ldg(T0 + (size_t)min(r, R0 - 1) * dc0);
+#pragma unroll
+            for (int a = 0; a < KC; ++a) s2 = fma(x[a], w0[a], s2);
+            ldl_solve<KC>(L, dinv, x);
+#pragma unroll
+            for (int a = 0; a < KC; ++a) M[rr][a] = x[a];
+            const bool isa = r < P.mi && mask_test(mk, r);
+            amask |= (isa ? 1u : 0u) << rr;
+            v[rr] = (r < R0 && !isa) ? s2 : -1e300;  // parked: never the maximum
+        }
+        bool feasible = false;
+        int rechecks = 0, nlog = 0, wref = 0;
+        for (int it = 0; it < max_iter; ++it) {
+            // arg-max in one 32-bit reduction: the key of a residual is the high word of the double with the row index in
+            // its 7 low bits (parked and satisfied rows have negative keys)
+            int kmax = 0;
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) kmax = max(kmax, (__double2hiint(v[rr]) & ~127) | kid[rr]);
+            const int wkey = __reduce_max_sync(PPG_FULL, kmax);
+            if (wkey <= ktol) {
+                // ---- exact verification in Gram space (see header of this kernel): replay the step log
+                __syncwarp();   // lane 0's log / fac stores
+                double s[RPL];
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr) s[rr] = -__ldg(T0 + (size_t)min(rr * 32 + lane, R0 - 1) * dc0);
+                double t = 0.0;  // lanes < k: Gam[A_lane, T] c_T
+                const unsigned long long gact = (unsigned long long)(Gam + act_lane);
+                for (int e = 0; e < nlog; ++e) {
+                    const double tk = lg[e];
+                    const unsigned off = (unsigned)((__double2loint(tk) & 127) * R0);
+                    const double* rp = reinterpret_cast<const double*>(glane) + off;
+#pragma unroll
+                    for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(-tk, __ldg(rp + r2 * 32), s[r2]);
+                    t = fma(-tk, __ldg(reinterpret_cast<const double*>(gact) + off), t);
+                }
+                const double rb = __ldg(T0 + (size_t)act_lane * dc0) - t;
+                double x[KC];
+#pragma unroll
+                for (int b = 0; b < KC; ++b) {
+                    x[b] = shfl_d(rb, b);
+                    if (!EXACT && b >= k) x[b] = 0.0;
+                }
+                {
+                    double Lv[KC][KC], dv[KC];
+                    int o = 0;
+#pragma unroll
+                    for (int i = 0; i < KC; ++i) {
+#pragma unroll
+                        for (int j = 0; j < KC; ++j) if (j < i) Lv[i][j] = fac[o++];
+                    }
+#pragma unroll
+                    for (int i = 0; i < KC; ++i) dv[i] = fac[NL + i];
+                    ldl_solve<KC>(Lv, dv, x);
+                }
+#pragma unroll
+                for (int a = 0; a < KC; ++a) {
+#pragma unroll
+                    for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(x[a], K2A_GP(a, lane + r2 * 32), s[r2]);
+                }
+                double worst = 0.0;
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr) {
+                    const int r = rr * 32 + lane;
+                    const bool isa = (amask >> rr) & 1u;
+                    if (r < R0) worst = dmax2(worst, isa ? fabs(s[rr]) : s[rr]);
+                    v[rr] = (r < R0 && !isa) ? s[rr] : -1e300;
+                }
+                worst = warp_max_nonneg(dmax2(worst, 0.0));
+                if (worst <= PPG_FEAS_TOL) { feasible = true; break; }
+                if (++rechecks > 3) break;
+                continue;
+            }
+            const int irow = wkey & 127;   // a most violated row (to 13 mantissa bits)
+            const int wl = irow & 31, wslot = irow >> 5;
+            const double wmax = __hiloint2double(wkey & ~127, 0);   // its violation, rounded down by < 2^-13
+            // stall detector: a relaxation that has not halved its worst violation in 16 steps is not going to finish
+            // inside the budget (badly scaled or zero-margin sets) -> simplex.  Halving = exponent - 1 = key - 2^20.
+            if ((it & 15) == 0) {
+                if (it != 0 && wkey > wref - 0x100000) break;
+                wref = wkey;
+            }
+            double g2[KC];
+#pragma unroll
+            for (int a = 0; a < KC; ++a) g2[a] = K2A_GP(a, irow);  // broadcast loads (padded slots: M == 0)
+            const double* rowp = reinterpret_cast<const double*>(glane) + (unsigned)(irow * R0);
+            double c2[RPL];
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) {
+                double x2 = __ldg(rowp + rr * 32);
+#pragma unroll
+                for (int a = 0; a < KC; ++a) x2 = fma(-M[rr][a], g2[a], x2);
+                c2[rr] = x2;
+            }
+            double mycol = c2[0];
+#pragma unroll
+            for (int rr = 1; rr < RPL; ++rr) if (rr == wslot) mycol = c2[rr];
+            const double nn = shfl_d(mycol, wl);   // |N g_i|^2
+            if (!(nn > 1e-12)) break;              // row i lies in the span of the active rows: leave it to the LP
+            // z -= tau (g_i - G_A' w).  tau needs no accuracy (fp32 reciprocal); its low mantissa bits carry the row
+            const double tau = k2a_key((K2A_OMEGA * wmax) * (double)rcp_approx((float)nn), irow);
+            // every lane stores the same word to the same address: no predicate, no branch
+            asm volatile("st.shared.f64 [%0], %1;" :: "r"(lg_sa + 8u * (unsigned)nlog), "d"(tau) : "memory");
+            ++nlog;
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) v[rr] = fma(-tau, c2[rr], v[rr]);
+        }
+#undef K2A_GP
+        n_it += (unsigned)nlog;
+        if (feasible) {
+            ++n_ok;
+            if (lane == 0) status[idx] = st | PPG_ST_FEAS;
+        }
+    }
+    if (lane == 0 && n_try) {
+        atomicAdd(&counters[CNT_K2A_TRIED], n_try);
+        atomicAdd(&counters[CNT_K2A_CERTIFIED], n_ok);
+        atomicAdd(&counters[CNT_K2A_STEPS], n_it);
+        atomicAdd(&counters[CNT_K2A_WORK], n_it * (unsigned long long)(R0 * (k + 1)));
+    }
+}
+
+template <int RPL, int KC, bool EXACT>
+static cudaError_t launch_k2a_reg(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                                  unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count,
+                                  cudaStream_t st) {
+    auto kern = k2a_relax_reg_kernel<RPL, KC, EXACT>;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    long long grid = (long long)sm_count * occ;
+    const long long need = (n + 3) / 4;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 128, 0, st>>>(P, masks, n, k_act, status, queue, counters, max_iter);
+    return cudaGetLastError();
+}
+
+template <int KC>
+static cudaError_t launch_k2a_reg_k(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                                    unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count,
+                                    cudaStream_t st) {
+#define K2A_REG(RPLV)                                                                                                       \
+    return k_act == KC ? launch_k2a_reg<RPLV, KC, true>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st) \
+                       : launch_k2a_reg<RPLV, KC, false>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
+    if (P.R0 <= 32) { K2A_REG(1) }
+    if (P.R0 <= 64) { K2A_REG(2) }
+    K2A_REG(4)
+#undef K2A_REG
+}
+
 #define K2A_SMALL(KCV)                                                                                                   \
     if (P.R0 <= 32) return launch_k2a_small<1, KCV>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);  \
     if (P.R0 <= 64) return launch_k2a_small<2, KCV>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);  \
@@ -509,6 +802,14 @@ static cudaError_t launch_k2a_small(const DevProgram& P, const uint64_t* masks, 
 cudaError_t launch_k2a(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count, cudaStream_t st) {
     if (k_act > 32 || P.nfree > 64) return cudaSuccess;  // outside the certificate kernel's envelope: K2 decides alone
+    static const int variant = getenv("PPGPU_K2A_V") ? atoi(getenv("PPGPU_K2A_V")) : 2;
+    if (variant == 2 && k_act >= 1 && k_act <= 8 && P.R0 <= 128) {
+        if (k_act <= 3) return launch_k2a_reg_k<3>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
+        if (k_act == 4) return launch_k2a_reg_k<4>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
+        if (k_act == 5) return launch_k2a_reg_k<5>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
+        if (k_act == 6) return launch_k2a_reg_k<6>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
+        return launch_k2a_reg_k<8>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
+    }
     if (k_act >= 1 && k_act <= 3 && P.R0 <= 128) { K2A_SMALL(3) }
     if (k_act == 4 && P.R0 <= 128) { K2A_SMALL(4) }
     if (k_act == 5 && P.R0 <= 128) { K2A_SMALL(5) }

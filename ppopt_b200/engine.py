@@ -261,8 +261,9 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
     (mpqp_parrallel_combinatorial.py:103-104).  ``max_levels`` caps the depth for programs nobody can finish
     (applied identically to the CPU baselines in bench.py).
 
-    Under torch.distributed (world size G > 1) every level's candidate array is cut into G contiguous slices, rank g
-    evaluates slice g, the status bytes are all-gathered (NCCL), and every rank then generates the identical next level.
+    Under torch.distributed (world size G > 1) every level's candidate array is cut into chunks dealt round-robin to the
+    ranks (sharding.py), the status bytes are combined by one NCCL all-reduce, and every rank then generates the identical
+    next level.
     """
     own = engine is None
     eng = Engine(program_arrays(program)) if own else engine
@@ -284,9 +285,9 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         k_act = lvl + 1
         status = torch.zeros((n,), dtype=torch.uint8, device=eng.tdev)
         if world > 1:
-            lo, hi, _ = sharding.slice_bounds(n, rank, world)
-            eng.level_eval(masks, k_act, status, 7, lo, hi)
-            status = sharding.gather_status(status, n, dist, rank, world)
+            for lo, hi in sharding.chunks(n, rank, world):
+                eng.level_eval(masks, k_act, status, 7, lo, hi)
+            status = sharding.gather_status(status, dist)
         else:
             eng.level_eval(masks, k_act, status, 7)
         n_reg = 0

@@ -2,34 +2,45 @@
 
 Within a level every candidate is independent (the reference itself maps them over a process pool,
 /root/reference/src/ppopt/mp_solvers/mpqp_parrallel_combinatorial.py:116); the only exchange is the per-candidate
-status byte that next-level generation needs.  Rank g owns the contiguous slice g of the (lexicographically ordered)
-candidate array; one all-gather of status bytes per level makes every rank hold all statuses, after which each rank
-regenerates the identical next level (K6 is deterministic and replicated).  No numerical data is ever reduced.
+status byte that next-level generation needs.  The candidate array (lexicographic order) is cut into world x CHUNKS
+contiguous chunks dealt round-robin to the ranks - the expensive candidates cluster in index ranges (sets containing the
+same leading rows), so plain contiguous slices left the slowest rank 15 % behind (measured at 4 GPUs).  Every rank
+evaluates its chunks in place in a full-length status vector that is zero elsewhere; one all-reduce(SUM) of the byte
+vector then gives every rank all statuses, after which each rank regenerates the identical next level (K6 is
+deterministic and replicated).  No numerical data is ever reduced.
 """
-from typing import Tuple
+from typing import List, Tuple
 
 import torch
 
-
-def slice_bounds(n: int, rank: int, world: int) -> Tuple[int, int, int]:
-    """(lo, hi, per): rank's slice [lo, hi) of n candidates cut into `world` contiguous slices of `per` (last ragged)."""
-    per = (n + world - 1) // world if world > 0 else n
-    lo = min(n, rank * per)
-    hi = min(n, lo + per)
-    return lo, hi, per
+CHUNKS_PER_RANK = 8
+MIN_CHUNK = 4096
 
 
-def gather_status(status: torch.Tensor, n: int, dist, rank: int, world: int) -> torch.Tensor:
-    """All ranks end with the full status vector: rank r contributes status[lo_r:hi_r] (padded to `per`)."""
-    lo, hi, per = slice_bounds(n, rank, world)
-    padded = torch.zeros((per,), dtype=torch.uint8, device=status.device)
-    padded[:hi - lo] = status[lo:hi]
-    parts = [torch.empty((per,), dtype=torch.uint8, device=status.device) for _ in range(world)]
-    dist.all_gather(parts, padded)
-    return torch.cat(parts)[:n].contiguous()
+def chunks(n: int, rank: int, world: int) -> List[Tuple[int, int]]:
+    """[lo, hi) ranges of the candidates rank evaluates; the ranges of all ranks tile [0, n) exactly"""
+    if world <= 1:
+        return [(0, n)] if n > 0 else []
+    per_rank = max(1, min(CHUNKS_PER_RANK, n // (world * MIN_CHUNK)))
+    total = world * per_rank
+    size = (n + total - 1) // total if n > 0 else 0
+    out = []
+    for j in range(rank, total, world):
+        lo, hi = min(n, j * size), min(n, (j + 1) * size)
+        if hi > lo:
+            out.append((lo, hi))
+    return out
+
+
+def gather_status(status: torch.Tensor, dist) -> torch.Tensor:
+    """status holds this rank's chunks and zeros elsewhere; afterwards every rank holds every byte"""
+    dist.all_reduce(status, op=dist.ReduceOp.SUM)
+    return status
 
 
 def owned(indices: torch.Tensor, n: int, rank: int, world: int) -> torch.Tensor:
-    """subset of (ascending) candidate indices that fall in rank's slice"""
-    lo, hi, _ = slice_bounds(n, rank, world)
-    return indices[(indices >= lo) & (indices < hi)].contiguous()
+    """subset of (ascending) candidate indices that fall in rank's chunks"""
+    keep = torch.zeros_like(indices, dtype=torch.bool)
+    for lo, hi in chunks(n, rank, world):
+        keep |= (indices >= lo) & (indices < hi)
+    return indices[keep].contiguous()

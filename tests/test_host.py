@@ -95,16 +95,19 @@ def test_engine_fails_loudly_without_gpu():
         solve_mpqp(load_presolved(os.path.join(GOLDEN, 'factory_mpqp.npz')))
 
 
-def test_slice_bounds_cover_exactly():
-    from ppopt_b200.sharding import slice_bounds
-    for n in (0, 1, 5, 16, 17, 1000):
+def test_chunks_tile_the_level_exactly():
+    from ppopt_b200.sharding import chunks
+    for n in (0, 1, 5, 16, 17, 1000, 70000, 1234567):
         for world in (1, 2, 3, 8):
             seen = []
             for r in range(world):
-                lo, hi, per = slice_bounds(n, r, world)
-                assert 0 <= lo <= hi <= n and hi - lo <= per
-                seen.extend(range(lo, hi))
-            assert seen == list(range(n))
+                for lo, hi in chunks(n, r, world):
+                    assert 0 <= lo < hi <= n
+                    seen.append((lo, hi))
+            seen.sort()
+            assert [x for lo, hi in seen for x in (lo, hi)] == ([0] + [b for _, b in seen[:-1] for b in (b, b)] + [n] if seen else [])
+            if n >= 8 * 4096 * world and world > 1:
+                assert all(len(chunks(n, r, world)) == 8 for r in range(world))
 
 
 WORKER = r'''
@@ -119,11 +122,10 @@ path = os.path.join(sys.argv[1], 'tests', 'golden', 'mpc_n3.npz')
 g = numpy.load(path); tw = twin_binding.Twin.from_npz(path)
 for lv in range(int(g['n_levels'])):
     cands = g[f'level{lv}_candidates']; n = len(cands)
-    lo, hi, per = sharding.slice_bounds(n, rank, world)
     status = torch.zeros(n, dtype=torch.uint8)
-    if hi > lo:
+    for lo, hi in sharding.chunks(n, rank, world):
         status[lo:hi] = torch.from_numpy(tw.eval(tw.masks(cands[lo:hi].tolist())))
-    full = sharding.gather_status(status, n, dist, rank, world)
+    full = sharding.gather_status(status, dist)
     assert numpy.array_equal(full.numpy() & 11, g[f'level{lv}_status'] & 11), (rank, lv)
     idx = torch.nonzero(full & 8).flatten()
     mine = sharding.owned(idx, n, rank, world)
@@ -135,8 +137,8 @@ print('ok', rank)
 
 
 def test_level_sharding_world_size_2_gloo(tmp_path):
-    """N>1 host path on CPU: each rank evaluates its slice (CPU checker standing in for the kernels), status bytes
-    are all-gathered over gloo, every rank ends with the reference's full status vector."""
+    """N>1 host path on CPU: each rank evaluates its chunks (CPU checker standing in for the kernels), status bytes
+    are all-reduced over gloo, every rank ends with the reference's full status vector."""
     script = tmp_path / 'worker.py'
     script.write_text(WORKER)
     port = str(29500 + os.getpid() % 2000)
