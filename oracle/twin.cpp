@@ -526,6 +526,31 @@ void twin_eval(void* h, const uint64_t* masks, long ncand, int final_level_lp, u
     }
 }
 
+// experiment hook: feasibility LP of one active set with an optional replacement rhs column (warm origin); returns
+// feasible flag, writes pivots; also exports the reduced feasibility rows for CPU emulations
+int twin_feas_rhs(void* h, const int* act, int k, const double* rhs, int* pivots_out) {
+    Twin& tw = *(Twin*)h;
+    const ReducedProgram& P = tw.P;
+    Lp lp;
+    lp_init(lp, P.R0, P.nfree);
+    const int dc = P.nfree + 2;
+    for (int i = 0; i < P.R0; ++i)
+        for (int c = 0; c < dc; ++c) lp.at(i, c) = P.T0[(size_t)i * dc + c];
+    if (rhs) for (int i = 0; i < P.R0; ++i) lp.at(i, 0) = rhs[i];
+    for (int j = 0; j < k; ++j) { lp.rowflag[act[j]] = 2; lp.at(act[j], lp.js) = 0.0; }
+    LpResult res = lp_maxmin(lp, -PPG_FEAS_TOL, false);
+    if (pivots_out) *pivots_out = lp.pivots;
+    if (res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED) return 1;
+    if (res.code == PPG_LP_OPTIMAL) return res.beta >= -PPG_FEAS_TOL;
+    return 0;
+}
+int twin_rows(void* h) { return ((Twin*)h)->P.R0; }
+int twin_nfree(void* h) { return ((Twin*)h)->P.nfree; }
+void twin_t0(void* h, double* out) {
+    const ReducedProgram& P = ((Twin*)h)->P;
+    for (size_t i = 0; i < P.T0.size(); ++i) out[i] = P.T0[i];
+}
+
 int twin_emit(void* h, const uint64_t* mask, double* laws_out, double* rows_out, int32_t* flags_out, double* info) {
     Twin& tw = *(Twin*)h;
     std::vector<int> act;

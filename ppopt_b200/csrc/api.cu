@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,11 @@ struct ppgpu_program {
     struct Span { int family; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
+    // K2a -> K2 warm hand-over buffers (grown on demand)
+    long long warm_cap = 0;
+    double* d_warm_resid = nullptr;
+    long long* d_warm_idx = nullptr;
+    unsigned long long* d_warm_count = nullptr;
     double prof_ms[PPGPU_NUM_FAMILIES] = {0};
     long long prof_launches[PPGPU_NUM_FAMILIES] = {0};
 };
@@ -48,6 +54,7 @@ struct ProfScope {
 };
 
 static const int QUEUE_SLOTS = 64;
+extern "C" { static void warm_release(ppgpu_program* p); }
 
 static int fail(const char* where, cudaError_t e) {
     g_err = std::string(where) + ": " + cudaGetErrorString(e);
@@ -125,6 +132,7 @@ int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, 
 int ppgpu_program_destroy(ppgpu_program* p) {
     if (!p) return 0;
     for (void* d : p->allocs) cudaFree(d);
+    warm_release(p);
     for (auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     delete p;
@@ -152,11 +160,65 @@ int ppgpu_root_level(ppgpu_program* p, uint64_t* d_masks, int64_t* h_count, ppgp
     return 0;
 }
 
-int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
-                     int32_t stages, ppgpu_stream stream) {
-    if (!p) return fail_msg("null argument");
-    if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
+// candidates of one ppgpu_level_eval call are processed in chunks of this many, so that the K2a -> K2 hand-over buffers
+// (one residual vector per uncertified candidate) stay bounded however large the level is
+static long long level_chunk() {
+    static const long long c = getenv("PPGPU_CHUNK") ? atoll(getenv("PPGPU_CHUNK")) : (1ll << 22);
+    return c < 1024 ? 1024 : c;
+}
+
+// Hand-over buffers are recycled through a small process-wide pool: a solve creates a program, runs a handful of levels
+// and destroys it, and cudaMalloc/cudaFree of a few hundred MB per solve cost more than the kernels of small programs.
+// A buffer belongs to exactly one live program at a time.
+struct WarmBuf { int device; size_t resid_bytes, idx_bytes; double* resid; long long* idx; };
+static std::mutex g_pool_mu;
+static std::vector<WarmBuf> g_pool;
+
+static void warm_release(ppgpu_program* p) {
+    if (!p->d_warm_resid) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool.size() < 4) {
+        g_pool.push_back({p->device, (size_t)p->warm_cap * p->dev.R0 * sizeof(double),
+                          (size_t)p->warm_cap * sizeof(long long), p->d_warm_resid, p->d_warm_idx});
+    } else {
+        cudaFree(p->d_warm_resid);
+        cudaFree(p->d_warm_idx);
+    }
+    p->d_warm_resid = nullptr; p->d_warm_idx = nullptr; p->warm_cap = 0;
+}
+
+static cudaError_t ensure_warm(ppgpu_program* p, long long cap, cudaStream_t st) {
+    if (!p->d_warm_count) {
+        cudaError_t e = cudaMalloc((void**)&p->d_warm_count, sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+        p->allocs.push_back(p->d_warm_count);
+    }
+    if (cap <= p->warm_cap) return cudaSuccess;
+    // two sizes only (small levels / full chunks), so a solve grows its buffers at most twice
+    const long long full = 4096 + level_chunk() / 8;
+    const long long want = cap <= 65536 ? 65536 : (cap > full ? cap : full);
+    cudaError_t e = cudaStreamSynchronize(st);   // earlier launches may still read the old buffers
+    if (e != cudaSuccess) return e;
+    warm_release(p);
+    const size_t rb = (size_t)want * p->dev.R0 * sizeof(double), ib = (size_t)want * sizeof(long long);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); ++i) {
+            if (g_pool[i].device == p->device && g_pool[i].resid_bytes >= rb && g_pool[i].idx_bytes >= ib) {
+                p->d_warm_resid = g_pool[i].resid; p->d_warm_idx = g_pool[i].idx; p->warm_cap = want;
+                g_pool.erase(g_pool.begin() + i);
+                return cudaSuccess;
+            }
+        }
+    }
+    if ((e = cudaMalloc((void**)&p->d_warm_resid, rb)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&p->d_warm_idx, ib)) != cudaSuccess) { cudaFree(p->d_warm_resid); p->d_warm_resid = nullptr; return e; }
+    p->warm_cap = want;
+    return cudaSuccess;
+}
+
+static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
+                            int32_t stages, cudaStream_t st) {
     cudaError_t e;
     if (stages & 1) {
         ProfScope ps(p, st, 0);
@@ -165,11 +227,20 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
         if (k_act >= 1 && k_act <= 8) p->launches++;  // prefilter + QR
         p->launches++;
     }
+    static const int warm_on = getenv("PPGPU_WARM") ? atoi(getenv("PPGPU_WARM")) : 1;
+    p->dev.warm_count = nullptr; p->dev.warm_resid = nullptr; p->dev.warm_idx = nullptr; p->dev.warm_cap = 0;
     if ((stages & 2) && !(stages & 8)) {
-        // feasibility certificates first (cheap); the simplex only sees what is left
+        // feasibility certificates first (cheap); the simplex only sees what is left, and starts from K2a's last iterate
         ProfScope ps(p, st, 7);
         static const int iters = getenv("PPGPU_K2A_ITERS") ? atoi(getenv("PPGPU_K2A_ITERS")) : 96;
         if (iters > 0 && k_act >= 0) {
+            if (warm_on) {
+                const long long cap = n < 4096 ? n : 4096 + n / 8;
+                if ((e = ensure_warm(p, cap, st)) != cudaSuccess) return fail("warm-start buffers", e);
+                p->dev.warm_count = p->d_warm_count; p->dev.warm_resid = p->d_warm_resid;
+                p->dev.warm_idx = p->d_warm_idx; p->dev.warm_cap = cap;
+                cudaMemsetAsync(p->d_warm_count, 0, sizeof(unsigned long long), st);
+            }
             e = launch_k2a(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, iters,
                            p->sm_count, st);
             if (e != cudaSuccess) return fail("K2a relaxation", e);
@@ -181,6 +252,12 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
         e = launch_k2(p->dev, d_masks, n, d_status, next_queue(p, st), p->d_counters, p->sm_count, st);
         if (e != cudaSuccess) return fail("K2 feasibility", e);
         p->launches++;
+        if (p->dev.warm_count) {
+            // candidates the warm solve found infeasible keep their hand-over mark until here, so that the cold scan of
+            // the same launch does not solve them a second time
+            if ((e = launch_clear_bits(d_status, n, PPG_ST_PRE, st)) != cudaSuccess) return fail("status clean-up", e);
+            p->launches++;
+        }
     }
     if (stages & 4) {
         ProfScope ps(p, st, 2);
@@ -192,6 +269,20 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
         }
         if (e != cudaSuccess) return fail("K3/K4 optimality screen", e);
         p->launches++;
+    }
+    return 0;
+}
+
+int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
+                     int32_t stages, ppgpu_stream stream) {
+    if (!p) return fail_msg("null argument");
+    if (n <= 0) return 0;
+    const long long chunk = level_chunk();
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t nn = n - off < chunk ? n - off : chunk;
+        const int rc = level_eval_chunk(p, d_masks + (size_t)off * p->dev.W, nn, k_act, d_status + off, stages,
+                                        (cudaStream_t)stream);
+        if (rc) return rc;
     }
     return 0;
 }

@@ -23,6 +23,12 @@ struct DevProgram {
     const double* A; const double* b; const double* F;      // originals (K5)
     const double* A_t; const double* b_t;
     const double* Q; const double* c; const double* H;
+    // K2a -> K2 hand-over (api.cu owns the buffers; null/0 = disabled): candidates the relaxation could not certify leave
+    // the exact residuals G z* - h of their last iterate here, and the simplex starts from z* instead of the origin
+    double* warm_resid;               // warm_cap x R0
+    long long* warm_idx;              // warm_cap candidate indices
+    unsigned long long* warm_count;   // slots handed out (may exceed warm_cap: the overflow goes the cold way)
+    long long warm_cap;
 };
 
 // indices into the device counter array (uint64 each)

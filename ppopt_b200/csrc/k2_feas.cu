@@ -36,21 +36,33 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
     typename Core::Shared& sh = sh_all[grp];
     unsigned long long n_lp = 0, n_piv = 0, n_work = 0, n_num = 0;
     const int W = P.W;
+    // work items: first the candidates K2a handed over with a warm origin (slot list), then the whole level
+    long long nwarm = 0;
+    if (P.warm_count != nullptr) {
+        const unsigned long long c = *P.warm_count;
+        nwarm = c < (unsigned long long)P.warm_cap ? (long long)c : P.warm_cap;
+    }
+    const long long total = nwarm + n;
     for (;;) {
-        long long idx;
+        long long item;
         if constexpr (NW == 1) {
             unsigned long long v = 0;
             if (tid == 0) v = atomicAdd(queue, 1ull);
-            idx = (long long)__shfl_sync(PPG_FULL, v, 0);
+            item = (long long)__shfl_sync(PPG_FULL, v, 0);
         } else {
             if (tid == 0) next_item[0] = (long long)atomicAdd(queue, 1ull);
             __syncthreads();
-            idx = next_item[0];
+            item = next_item[0];
             __syncthreads();
         }
-        if (idx >= n) break;
+        if (item >= total) break;
+        const bool warm = item < nwarm;
+        const long long idx = warm ? P.warm_idx[item] : item - nwarm;
+        if (idx < 0) continue;   // slot K2a could not fill (non-finite iterate): that candidate goes the cold way
+        const double* wres = warm ? P.warm_resid + (size_t)item * P.R0 : nullptr;
         const uint8_t st = status[idx];
-        if (!(st & PPG_ST_RANK) || (st & PPG_ST_FEAS)) continue;  // rank deficient, or already certified by K2a
+        // rank deficient, already certified by K2a, or waiting in the warm list (PPG_ST_PRE)
+        if (!warm && (!(st & PPG_ST_RANK) || (st & (PPG_ST_FEAS | PPG_ST_PRE)))) continue;
         const uint64_t* mk = masks + idx * W;
         double T[RPT][DC];
         int rflag[RPT];
@@ -62,6 +74,7 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
                 const double* src = P.T0 + (size_t)row * P.dc0;
 #pragma unroll
                 for (int c = 0; c < DC; ++c) T[rr][c] = (c < P.dc0) ? __ldg(src + c) : 0.0;
+                if (warm) T[rr][0] = -wres[row];   // h - G z*: the same LP seen from K2a's last iterate
                 rflag[rr] = 1;
                 if (row < P.mi && mask_test(mk, row)) {
                     rflag[rr] = 2;
@@ -77,7 +90,7 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
         const bool feas = res.code == PPG_LP_EARLY || res.code == PPG_LP_UNBOUNDED ||
                           (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_FEAS_TOL);
         if (tid == 0) {
-            uint8_t s2 = st;
+            uint8_t s2 = st;   // a hand-over mark (PPG_ST_PRE) stays: api.cu clears it after this launch
             if (feas) s2 |= PPG_ST_FEAS;
             if (res.code == PPG_LP_ITERLIM) { s2 |= PPG_ST_NUMERIC; n_num++; }
             status[idx] = s2;
@@ -144,6 +157,26 @@ static cudaError_t launch_k2_t(const DevProgram& P, const uint64_t* masks, long 
         case 40: return launch_k2_t<2, 2, 40>(P, masks, n, status, queue, counters, sm_count, st);     \
         default: return cudaErrorInvalidValue;                                                         \
     }
+
+__global__ void clear_bits_kernel(uint8_t* __restrict__ status, long long n, uint8_t bits) {
+    // 16 status bytes per thread
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i + 16 <= n && (reinterpret_cast<uintptr_t>(status + i) & 15) == 0) {
+        uint4 v = *reinterpret_cast<uint4*>(status + i);
+        const unsigned m = ~(0x01010101u * bits);
+        v.x &= m; v.y &= m; v.z &= m; v.w &= m;
+        *reinterpret_cast<uint4*>(status + i) = v;
+    } else {
+        for (long long j = i; j < n && j < i + 16; ++j) status[j] &= (uint8_t)~bits;
+    }
+}
+
+cudaError_t launch_clear_bits(uint8_t* status, long long n, uint8_t bits, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const long long threads = (n + 15) / 16;
+    clear_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(status, n, bits);
+    return cudaGetLastError();
+}
 
 int k2_pad_columns(int ncols_with_rhs) {
     const int opts[] = {8, 16, 24, 32, 40, 48, 64};

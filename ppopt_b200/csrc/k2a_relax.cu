@@ -576,14 +576,14 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
         // ---- active rows: lane a < k finds the a-th set bit, everybody gets all of them (padded slots repeat row 0)
         const int act_lane = mask_nth(mk, W, lane < k ? lane : 0);
         int act[KC];
-        unsigned long long gp[KC];   // address of Gam[act[a], 0]
+        unsigned gp[KC];   // element offset of Gam[act[a], 0] (32 bits: half the registers of a pointer)
 #pragma unroll
         for (int a = 0; a < KC; ++a) {
             act[a] = __shfl_sync(PPG_FULL, act_lane, (EXACT || a < k) ? a : 0);
-            gp[a] = (unsigned long long)(Gam + (size_t)act[a] * R0);
-            asm volatile("" : "+l"(gp[a]));
+            gp[a] = (unsigned)act[a] * (unsigned)R0;
+            asm volatile("" : "+r"(gp[a]));
         }
-#define K2A_GP(a, off) __ldg(reinterpret_cast<const double*>(gp[a]) + (off))
+#define K2A_GP(a, off) __ldg(Gam + (gp[a] + (unsigned)(off)))
         // ---- S = Gam[A,A] = L D L' (unit lower L), computed redundantly by every lane; padded slots form an identity block
         double L[KC][KC], dinv[KC];
         bool pd = true;
@@ -655,6 +655,46 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
         }
         bool feasible = false;
         int rechecks = 0, nlog = 0, wref = 0;
+        // exact residuals of the current iterate in Gram space (see header of this kernel): replay the step log
+        auto exact_residuals = [&](double (&s)[RPL]) {
+            __syncwarp();   // lane 0's fac stores, everybody's log stores
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) s[rr] = -__ldg(T0 + (size_t)min(rr * 32 + lane, R0 - 1) * dc0);
+            double t = 0.0;  // lanes < k: Gam[A_lane, T] c_T
+            const unsigned long long gact = (unsigned long long)(Gam + act_lane);
+            for (int e = 0; e < nlog; ++e) {
+                const double tk = lg[e];
+                const unsigned off = (unsigned)((__double2loint(tk) & 127) * R0);
+                const double* rp = reinterpret_cast<const double*>(glane) + off;
+#pragma unroll
+                for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(-tk, __ldg(rp + r2 * 32), s[r2]);
+                t = fma(-tk, __ldg(reinterpret_cast<const double*>(gact) + off), t);
+            }
+            const double rb = __ldg(T0 + (size_t)act_lane * dc0) - t;
+            double x[KC];
+#pragma unroll
+            for (int b = 0; b < KC; ++b) {
+                x[b] = shfl_d(rb, b);
+                if (!EXACT && b >= k) x[b] = 0.0;
+            }
+            {
+                double Lv[KC][KC], dv[KC];
+                int o = 0;
+#pragma unroll
+                for (int i = 0; i < KC; ++i) {
+#pragma unroll
+                    for (int j = 0; j < KC; ++j) if (j < i) Lv[i][j] = fac[o++];
+                }
+#pragma unroll
+                for (int i = 0; i < KC; ++i) dv[i] = fac[NL + i];
+                ldl_solve<KC>(Lv, dv, x);
+            }
+#pragma unroll
+            for (int a = 0; a < KC; ++a) {
+#pragma unroll
+                for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(x[a], K2A_GP(a, lane + r2 * 32), s[r2]);
+            }
+        };
         for (int it = 0; it < max_iter; ++it) {
             // arg-max in one 32-bit reduction: the key of a residual is the high word of the double with the row index in
             // its 7 low bits (parked and satisfied rows have negative keys)
@@ -663,45 +703,9 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
             for (int rr = 0; rr < RPL; ++rr) kmax = max(kmax, (__double2hiint(v[rr]) & ~127) | kid[rr]);
             const int wkey = __reduce_max_sync(PPG_FULL, kmax);
             if (wkey <= ktol) {
-                // ---- exact verification in Gram space (see header of this kernel): replay the step log
-                __syncwarp();   // lane 0's log / fac stores
+                // ---- exact verification
                 double s[RPL];
-#pragma unroll
-                for (int rr = 0; rr < RPL; ++rr) s[rr] = -__ldg(T0 + (size_t)min(rr * 32 + lane, R0 - 1) * dc0);
-                double t = 0.0;  // lanes < k: Gam[A_lane, T] c_T
-                const unsigned long long gact = (unsigned long long)(Gam + act_lane);
-                for (int e = 0; e < nlog; ++e) {
-                    const double tk = lg[e];
-                    const unsigned off = (unsigned)((__double2loint(tk) & 127) * R0);
-                    const double* rp = reinterpret_cast<const double*>(glane) + off;
-#pragma unroll
-                    for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(-tk, __ldg(rp + r2 * 32), s[r2]);
-                    t = fma(-tk, __ldg(reinterpret_cast<const double*>(gact) + off), t);
-                }
-                const double rb = __ldg(T0 + (size_t)act_lane * dc0) - t;
-                double x[KC];
-#pragma unroll
-                for (int b = 0; b < KC; ++b) {
-                    x[b] = shfl_d(rb, b);
-                    if (!EXACT && b >= k) x[b] = 0.0;
-                }
-                {
-                    double Lv[KC][KC], dv[KC];
-                    int o = 0;
-#pragma unroll
-                    for (int i = 0; i < KC; ++i) {
-#pragma unroll
-                        for (int j = 0; j < KC; ++j) if (j < i) Lv[i][j] = fac[o++];
-                    }
-#pragma unroll
-                    for (int i = 0; i < KC; ++i) dv[i] = fac[NL + i];
-                    ldl_solve<KC>(Lv, dv, x);
-                }
-#pragma unroll
-                for (int a = 0; a < KC; ++a) {
-#pragma unroll
-                    for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(x[a], K2A_GP(a, lane + r2 * 32), s[r2]);
-                }
+                exact_residuals(s);
                 double worst = 0.0;
 #pragma unroll
                 for (int rr = 0; rr < RPL; ++rr) {
@@ -741,20 +745,42 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
             for (int rr = 1; rr < RPL; ++rr) if (rr == wslot) mycol = c2[rr];
             const double nn = shfl_d(mycol, wl);   // |N g_i|^2
             if (!(nn > 1e-12)) break;              // row i lies in the span of the active rows: leave it to the LP
-            // z -= tau (g_i - G_A' w).  tau needs no accuracy (fp32 reciprocal); its low mantissa bits carry the row
-            const double tau = k2a_key((K2A_OMEGA * wmax) * (double)rcp_approx((float)nn), irow);
+            // z -= tau (g_i - G_A' w).  tau needs no accuracy; its low mantissa bits carry the row
+            double rnn;   // gross (20-bit) reciprocal: one MUFU instead of convert - rcp - convert
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rnn) : "d"(nn));
+            const double tau = k2a_key((K2A_OMEGA * wmax) * rnn, irow);
             // every lane stores the same word to the same address: no predicate, no branch
             asm volatile("st.shared.f64 [%0], %1;" :: "r"(lg_sa + 8u * (unsigned)nlog), "d"(tau) : "memory");
             ++nlog;
 #pragma unroll
             for (int rr = 0; rr < RPL; ++rr) v[rr] = fma(-tau, c2[rr], v[rr]);
         }
-#undef K2A_GP
         n_it += (unsigned)nlog;
         if (feasible) {
             ++n_ok;
             if (lane == 0) status[idx] = st | PPG_ST_FEAS;
+        } else if (P.warm_count != nullptr) {
+            // not certified: hand the last iterate to the simplex as its origin (exact residuals, any point will do)
+            double s[RPL];
+            exact_residuals(s);
+            unsigned long long slot = 0;
+            if (lane == 0) slot = atomicAdd(P.warm_count, 1ull);
+            slot = __shfl_sync(PPG_FULL, slot, 0);
+            bool fin = true;
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr) fin = fin && (rr * 32 + lane >= R0 || fabs(s[rr]) < 1e300);
+            fin = __all_sync(PPG_FULL, fin);
+            if (slot < (unsigned long long)P.warm_cap) {   // every slot handed out below the cap gets an index (-1: unused)
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr)
+                    if (fin && rr * 32 + lane < R0) P.warm_resid[slot * (unsigned long long)R0 + rr * 32 + lane] = s[rr];
+                if (lane == 0) {
+                    P.warm_idx[slot] = fin ? idx : -1;
+                    if (fin) status[idx] = st | PPG_ST_PRE;
+                }
+            }
         }
+#undef K2A_GP
     }
     if (lane == 0 && n_try) {
         atomicAdd(&counters[CNT_K2A_TRIED], n_try);

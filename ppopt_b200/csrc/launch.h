@@ -34,6 +34,8 @@ cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const lon
 cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, const uint64_t* survive,
                            const long long* offsets, long long nf, uint64_t* children, cudaStream_t st);
 
+cudaError_t launch_clear_bits(uint8_t* status, long long n, uint8_t bits, cudaStream_t st);
+
 cudaError_t measure_fp64_peak(int iters, double* tflops, cudaStream_t st);
 
 }  // namespace ppgpu
