@@ -96,6 +96,16 @@ int ppgpu_regions_emit(ppgpu_program* prog, const uint64_t* d_masks, const int64
 int ppgpu_children_count(ppgpu_program* prog, const uint64_t* d_masks, const int64_t* d_feas_idx, int64_t nf,
                          int32_t k_act, uint64_t* d_feas_masks, uint64_t* d_survive, int64_t* d_offsets,
                          int64_t* h_total, void* d_ws, size_t ws_bytes, ppgpu_stream stream);
+/* The same pass 1 in three steps, for callers that split the parents between GPUs: prepare gathers the
+ * parents and builds their hash set; count_range fills d_survive / d_counts for the parents [p_lo, p_hi) only (the
+ * caller zero-fills both and sums them across ranks); scan turns the counts (nf + 1 entries) into offsets. */
+int ppgpu_children_prepare(ppgpu_program* prog, const uint64_t* d_masks, const int64_t* d_feas_idx, int64_t nf,
+                           uint64_t* d_feas_masks, void* d_ws, size_t ws_bytes, ppgpu_stream stream);
+int ppgpu_children_count_range(ppgpu_program* prog, const uint64_t* d_feas_masks, int64_t nf, int32_t k_act,
+                               uint64_t* d_survive, int64_t* d_counts, int64_t p_lo, int64_t p_hi, void* d_ws,
+                               size_t ws_bytes, ppgpu_stream stream);
+int ppgpu_children_scan(ppgpu_program* prog, int64_t* d_counts_to_offsets, int64_t nf, int64_t* h_total, void* d_ws,
+                        size_t ws_bytes, ppgpu_stream stream);
 int ppgpu_children_write(ppgpu_program* prog, const uint64_t* d_feas_masks, const uint64_t* d_survive,
                          const int64_t* d_offsets, int64_t nf, uint64_t* d_children, ppgpu_stream stream);
 

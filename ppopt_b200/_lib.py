@@ -39,6 +39,9 @@ SYMBOLS = {
     'ppgpu_level_select': (ctypes.c_int, [_vp, _vp, _i64, _u8, _u8, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp]),
     'ppgpu_regions_emit': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ppgpu_children_count': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp]),
+    'ppgpu_children_prepare': (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    'ppgpu_children_count_range': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
+    'ppgpu_children_scan': (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64), _vp, _sz, _vp]),
     'ppgpu_children_write': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'ppgpu_counters': (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     'ppgpu_launch_count': (_i64, [_vp]),

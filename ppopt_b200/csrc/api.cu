@@ -352,6 +352,60 @@ int ppgpu_children_count(ppgpu_program* p, const uint64_t* d_masks, const int64_
     return 0;
 }
 
+int ppgpu_children_prepare(ppgpu_program* p, const uint64_t* d_masks, const int64_t* d_feas_idx, int64_t nf,
+                           uint64_t* d_feas_masks, void* d_ws, size_t ws_bytes, ppgpu_stream stream) {
+    if (!p) return fail_msg("null argument");
+    if (nf <= 0) return 0;
+    cudaError_t e;
+    {
+        ProfScope ps(p, (cudaStream_t)stream, 4);
+        e = children_prepare(p->dev, d_masks, (const long long*)d_feas_idx, nf, d_feas_masks, d_ws, ws_bytes, (cudaStream_t)stream);
+    }
+    if (e != cudaSuccess) return fail("K6 prepare", e);
+    p->launches += 3;
+    return 0;
+}
+
+int ppgpu_children_count_range(ppgpu_program* p, const uint64_t* d_feas_masks, int64_t nf, int32_t k_act,
+                               uint64_t* d_survive, int64_t* d_counts, int64_t p_lo, int64_t p_hi, void* d_ws,
+                               size_t ws_bytes, ppgpu_stream stream) {
+    if (!p) return fail_msg("null argument");
+    if (p_lo < 0 || p_hi > nf || p_lo > p_hi) return fail_msg("parent range outside [0, nf]");
+    if (nf <= 0 || p_hi == p_lo) return 0;
+    if (ws_bytes < scan_workspace_bytes(nf)) return fail_msg("workspace too small");
+    cudaError_t e;
+    {
+        ProfScope ps(p, (cudaStream_t)stream, 4);
+        e = children_count_range(p->dev, d_feas_masks, nf, k_act, d_survive, (long long*)d_counts, p_lo, p_hi, d_ws,
+                                 p->d_counters, (cudaStream_t)stream);
+    }
+    if (e != cudaSuccess) return fail("K6 count", e);
+    p->launches++;
+    return 0;
+}
+
+int ppgpu_children_scan(ppgpu_program* p, int64_t* d_counts_to_offsets, int64_t nf, int64_t* h_total, void* d_ws,
+                        size_t ws_bytes, ppgpu_stream stream) {
+    if (!p || !h_total) return fail_msg("null argument");
+    *h_total = 0;
+    if (nf <= 0) return 0;
+    if (ws_bytes < scan_workspace_bytes(nf)) return fail_msg("workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    {
+        ProfScope ps(p, st, 4);
+        e = children_scan((long long*)d_counts_to_offsets, nf, d_ws, st);
+    }
+    if (e != cudaSuccess) return fail("K6 scan", e);
+    p->launches += 2;
+    long long tot = 0;
+    e = cudaMemcpyAsync(&tot, (long long*)d_counts_to_offsets + nf, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("K6 total", e);
+    *h_total = tot;
+    return 0;
+}
+
 int ppgpu_children_write(ppgpu_program* p, const uint64_t* d_feas_masks, const uint64_t* d_survive,
                          const int64_t* d_offsets, int64_t nf, uint64_t* d_children, ppgpu_stream stream) {
     if (!p) return fail_msg("null argument");

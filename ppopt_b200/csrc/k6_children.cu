@@ -230,9 +230,9 @@ __device__ __forceinline__ bool hash_contains(const uint64_t* __restrict__ feas,
 }
 
 __global__ void __launch_bounds__(128)
-children_count_kernel(DevProgram P, const uint64_t* __restrict__ feas, long long nf, int k_act, uint64_t* __restrict__ survive,
-                      long long* __restrict__ counts, unsigned long long* __restrict__ counters,
-                      const int* __restrict__ table, unsigned cap_mask) {
+children_count_kernel(DevProgram P, const uint64_t* __restrict__ feas, long long p_lo, long long p_hi, int k_act,
+                      uint64_t* __restrict__ survive, long long* __restrict__ counts,
+                      unsigned long long* __restrict__ counters, const int* __restrict__ table, unsigned cap_mask) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -242,7 +242,7 @@ children_count_kernel(DevProgram P, const uint64_t* __restrict__ feas, long long
     const int child_limit = lp ? (P.ne + k_act + 1) + P.m - P.n : 0x7fffffff;   // global index bound for the child
     const int sub_limit = lp ? (P.ne + k_act) + P.m - P.n : 0x7fffffff;         // ... for its k-subsets
     unsigned long long lookups = 0;
-    for (long long p = warp0; p < nf; p += nwarps) {
+    for (long long p = p_lo + warp0; p < p_hi; p += nwarps) {
         uint64_t pm[MAXW];
 #pragma unroll
         for (int w = 0; w < MAXW; ++w) pm[w] = w < W ? feas[p * W + w] : 0ull;
@@ -319,15 +319,20 @@ children_write_kernel(int W, const uint64_t* __restrict__ feas, const uint64_t* 
 }
 
 // feas_masks (nf x W, sorted), survive (nf x W), offsets (nf + 1, exclusive scan of the per-parent child counts)
-cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const long long* feas_idx, long long nf, int k_act,
-                           uint64_t* feas_masks, uint64_t* survive, long long* offsets, void* ws, size_t ws_bytes,
-                           unsigned long long* counters, cudaStream_t st) {
-    if (P.W > MAXW) return cudaErrorInvalidValue;
-    if (nf == 0) return cudaMemsetAsync(offsets, 0, sizeof(long long), st);
-    const long long nb = (nf + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    if (nf >= (1ll << 30)) return cudaErrorInvalidValue;
+static unsigned hash_capacity(long long nf) {
     unsigned cap = 1024;
     while ((long long)cap < 2 * nf) cap <<= 1;          // load factor in (0.25, 0.5]
+    return cap;
+}
+
+// gathers the feasible parents and builds the hash set of their masks in the workspace (behind the scan scratch)
+cudaError_t children_prepare(const DevProgram& P, const uint64_t* masks, const long long* feas_idx, long long nf,
+                             uint64_t* feas_masks, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (P.W > MAXW) return cudaErrorInvalidValue;
+    if (nf <= 0) return cudaSuccess;
+    if (nf >= (1ll << 30)) return cudaErrorInvalidValue;
+    const long long nb = (nf + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const unsigned cap = hash_capacity(nf);
     if (ws_bytes < (size_t)(nb + 2) * sizeof(long long) + (size_t)cap * sizeof(int)) return cudaErrorInvalidValue;
     int* table = reinterpret_cast<int*>((long long*)ws + nb + 2);
     const long long ne = nf * P.W;
@@ -335,10 +340,37 @@ cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const lon
     cudaError_t e = cudaMemsetAsync(table, 0xff, (size_t)cap * sizeof(int), st);
     if (e != cudaSuccess) return e;
     hash_insert_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(feas_masks, nf, P.W, table, cap - 1);
-    long long blocks = (nf * 32 + 127) / 128;
+    return cudaGetLastError();
+}
+
+// surviving children (bit sets) and their number for the parents [p_lo, p_hi); other entries are left untouched
+cudaError_t children_count_range(const DevProgram& P, const uint64_t* feas_masks, long long nf, int k_act, uint64_t* survive,
+                                 long long* counts, long long p_lo, long long p_hi, void* ws, unsigned long long* counters,
+                                 cudaStream_t st) {
+    if (p_hi <= p_lo) return cudaSuccess;
+    const long long nb = (nf + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const unsigned cap = hash_capacity(nf);
+    const int* table = reinterpret_cast<const int*>((long long*)ws + nb + 2);
+    long long blocks = ((p_hi - p_lo) * 32 + 127) / 128;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    children_count_kernel<<<(unsigned)blocks, 128, 0, st>>>(P, feas_masks, nf, k_act, survive, offsets, counters, table, cap - 1);
-    return scan_inplace(offsets, nf, (long long*)ws, st);
+    children_count_kernel<<<(unsigned)blocks, 128, 0, st>>>(P, feas_masks, p_lo, p_hi, k_act, survive, counts, counters, table,
+                                                            cap - 1);
+    return cudaGetLastError();
+}
+
+cudaError_t children_scan(long long* counts_to_offsets, long long nf, void* ws, cudaStream_t st) {
+    if (nf == 0) return cudaMemsetAsync(counts_to_offsets, 0, sizeof(long long), st);
+    return scan_inplace(counts_to_offsets, nf, (long long*)ws, st);
+}
+
+cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const long long* feas_idx, long long nf, int k_act,
+                           uint64_t* feas_masks, uint64_t* survive, long long* offsets, void* ws, size_t ws_bytes,
+                           unsigned long long* counters, cudaStream_t st) {
+    if (nf == 0) return cudaMemsetAsync(offsets, 0, sizeof(long long), st);
+    cudaError_t e = children_prepare(P, masks, feas_idx, nf, feas_masks, ws, ws_bytes, st);
+    if (e != cudaSuccess) return e;
+    if ((e = children_count_range(P, feas_masks, nf, k_act, survive, offsets, 0, nf, ws, counters, st)) != cudaSuccess) return e;
+    return children_scan(offsets, nf, ws, st);
 }
 
 cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, const uint64_t* survive, const long long* offsets,

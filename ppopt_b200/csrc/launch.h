@@ -31,6 +31,12 @@ cudaError_t root_level(const DevProgram& P, uint64_t* masks, long long* d_count,
 cudaError_t children_count(const DevProgram& P, const uint64_t* masks, const long long* feas_idx, long long nf,
                            int k_act, uint64_t* feas_masks, uint64_t* survive, long long* offsets, void* ws,
                            size_t ws_bytes, unsigned long long* counters, cudaStream_t st);
+cudaError_t children_prepare(const DevProgram& P, const uint64_t* masks, const long long* feas_idx, long long nf,
+                             uint64_t* feas_masks, void* ws, size_t ws_bytes, cudaStream_t st);
+cudaError_t children_count_range(const DevProgram& P, const uint64_t* feas_masks, long long nf, int k_act, uint64_t* survive,
+                                 long long* counts, long long p_lo, long long p_hi, void* ws, unsigned long long* counters,
+                                 cudaStream_t st);
+cudaError_t children_scan(long long* counts_to_offsets, long long nf, void* ws, cudaStream_t st);
 cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, const uint64_t* survive,
                            const long long* offsets, long long nf, uint64_t* children, cudaStream_t st);
 

@@ -132,10 +132,14 @@ class Engine:
                                                self._stream()), 'regions_emit')
         return laws, rows, flags, info
 
-    def children(self, masks: torch.Tensor, feas_idx: torch.Tensor, k_act: int) -> torch.Tensor:
+    def children(self, masks: torch.Tensor, feas_idx: torch.Tensor, k_act: int, dist=None) -> torch.Tensor:
+        """next level's candidates; with dist (torch.distributed, world > 1) the pruning look-ups of the parents are split
+        between the ranks and the per-parent results summed (every rank ends up with the identical child array)"""
         nf = feas_idx.shape[0]
         if nf == 0:
             return self.empty((0, self.W), torch.int64)
+        if dist is not None and dist.get_world_size() > 1 and nf >= 65536:
+            return self._children_sharded(masks, feas_idx, k_act, dist)
         feas_masks = self.empty((nf, self.W), torch.int64)
         survive = self.empty((nf, self.W), torch.int64)
         offsets = self.empty((nf + 1,), torch.int64)
@@ -149,6 +153,31 @@ class Engine:
         out = self.empty((tot.value, self.W), torch.int64)
         if tot.value:
             _lib.check(self.lib.ppgpu_children_write(self.h, feas_masks.data_ptr(), survive.data_ptr(), offsets.data_ptr(),
+                                                     nf, out.data_ptr(), self._stream()), 'children_write')
+        return out
+
+    def _children_sharded(self, masks, feas_idx, k_act, dist):
+        from . import sharding
+        nf = feas_idx.shape[0]
+        feas_masks = self.empty((nf, self.W), torch.int64)
+        survive = torch.zeros((nf, self.W), dtype=torch.int64, device=self.tdev)
+        counts = torch.zeros((nf + 1,), dtype=torch.int64, device=self.tdev)
+        ws_bytes = self.lib.ppgpu_scan_workspace_bytes(nf)
+        ws = self.empty(((ws_bytes + 7) // 8,), torch.int64)
+        _lib.check(self.lib.ppgpu_children_prepare(self.h, masks.data_ptr(), feas_idx.data_ptr(), nf, feas_masks.data_ptr(),
+                                                   ws.data_ptr(), ws_bytes, self._stream()), 'children_prepare')
+        for lo, hi in sharding.chunks(nf, dist.get_rank(), dist.get_world_size()):
+            _lib.check(self.lib.ppgpu_children_count_range(self.h, feas_masks.data_ptr(), nf, k_act, survive.data_ptr(),
+                                                           counts.data_ptr(), lo, hi, ws.data_ptr(), ws_bytes,
+                                                           self._stream()), 'children_count_range')
+        dist.all_reduce(survive, op=dist.ReduceOp.SUM)   # disjoint supports: the sum is the union
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        tot = ctypes.c_int64(0)
+        _lib.check(self.lib.ppgpu_children_scan(self.h, counts.data_ptr(), nf, ctypes.byref(tot), ws.data_ptr(), ws_bytes,
+                                                self._stream()), 'children_scan')
+        out = self.empty((tot.value, self.W), torch.int64)
+        if tot.value:
+            _lib.check(self.lib.ppgpu_children_write(self.h, feas_masks.data_ptr(), survive.data_ptr(), counts.data_ptr(),
                                                      nf, out.data_ptr(), self._stream()), 'children_write')
         return out
 
@@ -323,7 +352,7 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         if collect_status:
             statuses.append((masks.cpu().numpy(), status.cpu().numpy()))
         last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
-        nxt = eng.children(masks, feas_idx, k_act) if not last else eng.empty((0, eng.W), torch.int64)
+        nxt = eng.children(masks, feas_idx, k_act, dist if world > 1 else None) if not last else eng.empty((0, eng.W), torch.int64)
         torch.cuda.synchronize(eng.tdev)
         total += n
         stats.append(dict(level=lvl + 1, candidates=n, feasible=n_feas, optimal=n_opt, regions=n_reg,

@@ -13,8 +13,8 @@ from typing import List, Tuple
 
 import torch
 
-CHUNKS_PER_RANK = 8
-MIN_CHUNK = 4096
+CHUNKS_PER_RANK = 32
+MIN_CHUNK = 16384
 
 
 def chunks(n: int, rank: int, world: int) -> List[Tuple[int, int]]:

@@ -112,6 +112,51 @@ def test_headline_size_properties():
     eng.close()
 
 
+def test_k6_split_between_ranks_equals_single_pass():
+    """the multi-GPU path counts the children of disjoint parent ranges on different ranks and sums the per-parent
+    results (engine._children_sharded): any split must reproduce the single-pass child array"""
+    import torch
+
+    engine, prog, eng = _engine('synthetic_30_6_40_s0')
+    g = numpy.load(os.path.join(GOLDEN, 'synthetic_30_6_40_s0.npz'))
+    masks = eng.masks_from_lists(g['level1_candidates'].tolist())
+    status = eng.level_eval(masks, 2)
+    rng = numpy.random.default_rng(3)
+    keep = torch.from_numpy(rng.random(masks.shape[0]) < 0.9).to(status.device)
+    feas_idx = torch.nonzero(((status & 2) != 0) & keep).flatten().contiguous()
+    whole = eng.children(masks, feas_idx, 2)
+    from ppopt_b200 import _lib, sharding
+    import ctypes
+    nf = feas_idx.shape[0]
+    for world in (2, 3):
+        feas_masks = eng.empty((nf, eng.W), torch.int64)
+        ws_bytes = eng.lib.ppgpu_scan_workspace_bytes(nf)
+        ws = eng.empty(((ws_bytes + 7) // 8,), torch.int64)
+        _lib.check(eng.lib.ppgpu_children_prepare(eng.h, masks.data_ptr(), feas_idx.data_ptr(), nf, feas_masks.data_ptr(),
+                                                  ws.data_ptr(), ws_bytes, eng._stream()), 'prepare')
+        survive_sum = torch.zeros((nf, eng.W), dtype=torch.int64, device=eng.tdev)
+        counts_sum = torch.zeros((nf + 1,), dtype=torch.int64, device=eng.tdev)
+        for rank in range(world):
+            survive = torch.zeros_like(survive_sum)
+            counts = torch.zeros_like(counts_sum)
+            bounds = [(nf * rank // world, nf * (rank + 1) // world)] if nf < 16384 * world else sharding.chunks(nf, rank, world)
+            for lo, hi in bounds:
+                _lib.check(eng.lib.ppgpu_children_count_range(eng.h, feas_masks.data_ptr(), nf, 2, survive.data_ptr(),
+                                                              counts.data_ptr(), lo, hi, ws.data_ptr(), ws_bytes,
+                                                              eng._stream()), 'count_range')
+            survive_sum += survive
+            counts_sum += counts
+        tot = ctypes.c_int64(0)
+        _lib.check(eng.lib.ppgpu_children_scan(eng.h, counts_sum.data_ptr(), nf, ctypes.byref(tot), ws.data_ptr(), ws_bytes,
+                                               eng._stream()), 'scan')
+        assert tot.value == whole.shape[0]
+        out = eng.empty((tot.value, eng.W), torch.int64)
+        _lib.check(eng.lib.ppgpu_children_write(eng.h, feas_masks.data_ptr(), survive_sum.data_ptr(), counts_sum.data_ptr(),
+                                                nf, out.data_ptr(), eng._stream()), 'write')
+        assert torch.equal(out, whole)
+    eng.close()
+
+
 def test_slice_evaluation_equals_whole_level():
     """the multi-GPU path evaluates [lo, hi) slices of a level: statuses must not depend on the slicing"""
     import torch
