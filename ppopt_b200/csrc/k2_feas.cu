@@ -26,11 +26,13 @@ constexpr int k2_min_blocks(int threads, int rpt, int dc) {
 template <int NW, int RPT, int DC, int WPC>
 __global__ void __launch_bounds__(NW * 32 * WPC, k2_min_blocks(NW * 32 * WPC, RPT, DC))
 k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, uint8_t* __restrict__ status,
-               unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters) {
+               unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int scan_pt) {
     typedef LpCore<NW, RPT, DC> Core;
     constexpr int GT = NW * 32;
     __shared__ typename Core::Shared sh_all[WPC];
     __shared__ long long next_item[WPC];
+    __shared__ int need_list[WPC][GT * 16];   // candidates of the scanned block that need an LP (offsets into the block)
+    __shared__ int need_cnt[WPC];
     const int grp = (NW == 1) ? (threadIdx.x >> 5) : 0;
     const int tid = (NW == 1) ? (threadIdx.x & 31) : threadIdx.x;
     typename Core::Shared& sh = sh_all[grp];
@@ -42,7 +44,12 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
         const unsigned long long c = *P.warm_count;
         nwarm = c < (unsigned long long)P.warm_cap ? (long long)c : P.warm_cap;
     }
-    const long long total = nwarm + n;
+    // then the level itself, scanned in blocks of GT * scan_pt status bytes per queue item: after K2a almost nothing is left
+    // (one atomic + one status load per CANDIDATE cost more than the LPs of the 2 % that needed one)
+    const int blk = GT * scan_pt;
+    const long long nblocks = (n + blk - 1) / blk;
+    const long long total = nwarm + nblocks;
+    auto group_sync = [&]() { if constexpr (NW == 1) __syncwarp(); else __syncthreads(); };
     for (;;) {
         long long item;
         if constexpr (NW == 1) {
@@ -57,12 +64,36 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
         }
         if (item >= total) break;
         const bool warm = item < nwarm;
-        const long long idx = warm ? P.warm_idx[item] : item - nwarm;
+        const long long base = warm ? 0 : (item - nwarm) * blk;
+        int nlist = 1;
+        if (!warm) {
+            if (tid == 0) need_cnt[grp] = 0;
+            group_sync();
+            const long long c0 = base + (long long)tid * scan_pt;
+            uint8_t sb[16];
+            if (scan_pt == 16 && c0 + 16 <= n && (reinterpret_cast<uintptr_t>(status + c0) & 15) == 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(status + c0);
+                const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sb[j] = (uint8_t)(w4[j >> 2] >> ((j & 3) * 8));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sb[j] = (j < scan_pt && c0 + j < n) ? status[c0 + j] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // needs an LP: full rank, not certified by K2a, not waiting in the warm list (PPG_ST_PRE)
+                if ((sb[j] & PPG_ST_RANK) && !(sb[j] & (PPG_ST_FEAS | PPG_ST_PRE)))
+                    need_list[grp][atomicAdd(&need_cnt[grp], 1)] = tid * scan_pt + j;
+            }
+            group_sync();
+            nlist = need_cnt[grp];
+        }
+        for (int li = 0; li < nlist; ++li) {
+        const long long idx = warm ? P.warm_idx[item] : base + need_list[grp][li];
         if (idx < 0) continue;   // slot K2a could not fill (non-finite iterate): that candidate goes the cold way
         const double* wres = warm ? P.warm_resid + (size_t)item * P.R0 : nullptr;
         const uint8_t st = status[idx];
-        // rank deficient, already certified by K2a, or waiting in the warm list (PPG_ST_PRE)
-        if (!warm && (!(st & PPG_ST_RANK) || (st & (PPG_ST_FEAS | PPG_ST_PRE)))) continue;
         const uint64_t* mk = masks + idx * W;
         double T[RPT][DC];
         int rflag[RPT];
@@ -97,6 +128,8 @@ k2_feas_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, ui
             n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
         }
         if constexpr (NW > 1) __syncthreads();
+        }
+        group_sync();   // need_list is rewritten by the next block
     }
     if (tid == 0 && n_lp) {
         atomicAdd(&counters[CNT_K2_LPS], n_lp);
@@ -119,7 +152,15 @@ static cudaError_t launch_k2_t(const DevProgram& P, const uint64_t* masks, long 
     long long grid = (long long)sm_count * occ;
     if (grid > groups_needed) grid = groups_needed;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, NW * 32 * WPC, 0, st>>>(P, masks, n, status, queue, counters);
+    // status bytes scanned per thread and queue item: 16 when K2a has been over the level (next to nothing is left), fewer
+    // when the simplex still owns most candidates and blocks must stay small enough to balance
+    int scan_pt = 1;
+    if (P.warm_count != nullptr) {
+        const long long groups = grid * WPC;
+        scan_pt = 16;
+        while (scan_pt > 1 && (n + (long long)NW * 32 * scan_pt - 1) / ((long long)NW * 32 * scan_pt) < 4 * groups) scan_pt >>= 1;
+    }
+    kern<<<(unsigned)grid, NW * 32 * WPC, 0, st>>>(P, masks, n, status, queue, counters, scan_pt);
     return cudaGetLastError();
 }
 
