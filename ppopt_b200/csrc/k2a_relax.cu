@@ -540,7 +540,7 @@ __device__ __forceinline__ double k2a_key(double v, int idx) {
 constexpr int K2A_LOG = 128;  // step log entries per warp (max_iter is clamped to it)
 
 template <int RPL, int KC, bool EXACT>
-__global__ void __launch_bounds__(128, (RPL * KC <= 16) ? 5 : ((RPL * KC <= 24) ? 4 : 3))
+__global__ void __launch_bounds__(128, (RPL * KC <= 16) ? 5 : ((RPL * KC <= 24) ? 4 : 3))   // 96 registers for 4 x 5 spill M: slower
 k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
                      unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter) {
     constexpr int NL = KC * (KC - 1) / 2;

@@ -124,7 +124,7 @@ static bool launch_k3p(const DevProgram& P, const uint64_t* masks, long long n, 
 template <int RPT, int DC, int WPC>
 __global__ void __launch_bounds__(32 * WPC)
 k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
-           unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int use_pre) {
+           unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int use_pre, int scan_pt) {
     typedef LpCore<1, RPT, DC> Core;
     extern __shared__ double dyn_smem[];
     __shared__ typename Core::Shared sh_all[WPC];
@@ -137,17 +137,42 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
     double* Lam = S + (size_t)kmax * kmax;
     int* act = reinterpret_cast<int*>(Lam + (size_t)kmax * t1);
     unsigned long long n_lp = 0, n_piv = 0, n_work = 0, n_num = 0;
+    // the level is scanned in blocks of 32 * scan_pt status bytes per queue item (the prefilter leaves a few per cent of
+    // the candidates: one atomic and one dependent status load per candidate would dominate)
+    const int blk = 32 * scan_pt;
+    const long long nblocks = (n + blk - 1) / blk;
     for (;;) {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(queue, 1ull);
-        const long long idx = (long long)__shfl_sync(PPG_FULL, v, 0);
-        if (idx >= n) break;
-        uint8_t st = status[idx];
-        if (!(st & PPG_ST_FEAS)) continue;
-        if (use_pre) {
-            if (!(st & PPG_ST_PRE)) continue;   // rejected by the thread-per-candidate prefilter
-            st &= (uint8_t)~PPG_ST_PRE;
+        const long long item = (long long)__shfl_sync(PPG_FULL, v, 0);
+        if (item >= nblocks) break;
+        const long long c0 = item * blk + (long long)lane * scan_pt;
+        unsigned need = 0;   // bit j: candidate c0 + j is feasible and passed the prefilter
+        {
+            uint8_t sb[16];
+            if (scan_pt == 16 && c0 + 16 <= n && (reinterpret_cast<uintptr_t>(status + c0) & 15) == 0) {
+                const uint4 q = *reinterpret_cast<const uint4*>(status + c0);
+                const unsigned w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sb[j] = (uint8_t)(w4[j >> 2] >> ((j & 3) * 8));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sb[j] = (j < scan_pt && c0 + j < n) ? status[c0 + j] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if ((sb[j] & PPG_ST_FEAS) && (!use_pre || (sb[j] & PPG_ST_PRE))) need |= 1u << j;
         }
+        for (;;) {
+        const unsigned bal = __ballot_sync(PPG_FULL, need != 0);
+        if (!bal) break;
+        const int src = __ffs((int)bal) - 1;
+        const unsigned nm = __shfl_sync(PPG_FULL, need, src);
+        const int jb = __ffs((int)nm) - 1;
+        if (lane == src) need &= need - 1;
+        const long long idx = item * blk + (long long)src * scan_pt + jb;
+        uint8_t st = status[idx];
+        if (use_pre) st &= (uint8_t)~PPG_ST_PRE;
         const uint64_t* mk = masks + idx * W;
         const int k = kmax;
         __syncwarp();
@@ -303,6 +328,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
             if (numeric) { s2 |= PPG_ST_NUMERIC; n_num++; }
             if (s2 != st || use_pre) status[idx] = s2;
         }
+        }
     }
     if (lane == 0 && (n_lp || n_num)) {
         atomicAdd(&counters[CNT_K4_LPS], n_lp);
@@ -332,7 +358,10 @@ static cudaError_t launch_k34_t(const DevProgram& P, const uint64_t* masks, long
     const long long need = (n + WPC - 1) / WPC;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 32 * WPC, smem, st>>>(P, masks, n, k_act, status, queue, counters, use_pre);
+    // one status byte per lane and queue item: 32x fewer atomics than one item per candidate, and still ~1 LP per item
+    // (16 bytes per lane measured slower: the survivors cluster and a warp then owns dozens of 100 us LPs in a row)
+    const int scan_pt = 1;
+    kern<<<(unsigned)grid, 32 * WPC, smem, st>>>(P, masks, n, k_act, status, queue, counters, use_pre, scan_pt);
     return cudaGetLastError();
 }
 
