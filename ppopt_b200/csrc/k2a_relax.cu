@@ -564,14 +564,29 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
 #pragma unroll
     for (int rr = 0; rr < RPL; ++rr) { kid[rr] = rr * 32 + lane; asm volatile("" : "+r"(kid[rr])); }
     unsigned long long n_try = 0, n_ok = 0, n_it = 0;
+    // A warp takes 32 consecutive candidates per queue item: every lane fetches the status byte and the mask words of one of
+    // them up front (the two dependent HBM round trips and the atomic are paid once per 32 candidates, not per candidate),
+    // the masks wait in shared memory, and the candidates that need work are then processed one after the other.
+    __shared__ uint64_t mk_s[4][32 * 4];
     for (;;) {
         unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(queue, 1ull);
-        const long long idx = (long long)__shfl_sync(PPG_FULL, q, 0);
-        if (idx >= n) break;
-        const uint8_t st = status[idx];
-        if (!(st & PPG_ST_RANK) || (st & PPG_ST_FEAS)) continue;
-        const uint64_t* mk = masks + idx * W;
+        if (lane == 0) q = atomicAdd(queue, 32ull);
+        const long long base = (long long)__shfl_sync(PPG_FULL, q, 0);
+        if (base >= n) break;
+        uint8_t st_l = 0;
+        __syncwarp();   // the previous batch's masks are no longer read
+        if (base + lane < n) {
+            st_l = status[base + lane];
+            for (int w = 0; w < W; ++w) mk_s[warp][lane * 4 + w] = masks[(base + lane) * W + w];
+        }
+        __syncwarp();
+        unsigned todo = __ballot_sync(PPG_FULL, (st_l & PPG_ST_RANK) && !(st_l & PPG_ST_FEAS));
+        while (todo) {
+        const int bj = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const long long idx = base + bj;
+        const uint8_t st = (uint8_t)__shfl_sync(PPG_FULL, (int)st_l, bj);
+        const uint64_t* mk = &mk_s[warp][bj * 4];
         ++n_try;
         // ---- active rows: lane a < k finds the a-th set bit, everybody gets all of them (padded slots repeat row 0)
         const int act_lane = mask_nth(mk, W, lane < k ? lane : 0);
@@ -781,6 +796,7 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
             }
         }
 #undef K2A_GP
+        }
     }
     if (lane == 0 && n_try) {
         atomicAdd(&counters[CNT_K2A_TRIED], n_try);
@@ -800,7 +816,7 @@ static cudaError_t launch_k2a_reg(const DevProgram& P, const uint64_t* masks, lo
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     long long grid = (long long)sm_count * occ;
-    const long long need = (n + 3) / 4;
+    const long long need = (n + 127) / 128;   // 32 candidates per warp and queue item
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, 128, 0, st>>>(P, masks, n, k_act, status, queue, counters, max_iter);
