@@ -537,12 +537,14 @@ __device__ __forceinline__ double k2a_key(double v, int idx) {
     return __hiloint2double(__double2hiint(v), (__double2loint(v) & ~127) | idx);
 }
 
-constexpr int K2A_LOG = 128;  // step log entries per warp (max_iter is clamped to it)
+constexpr int K2A_LOG = 192;       // step log entries per warp (both phases together are clamped to it)
+constexpr double K2A_OMEGA2 = 1.8; // second phase, see the step loop
+constexpr int K2A_STALL2 = 48;
 
 template <int RPL, int KC, bool EXACT>
 __global__ void __launch_bounds__(128, (RPL * KC <= 16) ? 5 : ((RPL * KC <= 24) ? 4 : 3))   // 96 registers for 4 x 5 spill M: slower
 k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
-                     unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter) {
+                     unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter, int max_iter2) {
     constexpr int NL = KC * (KC - 1) / 2;
     __shared__ double fac_s[4][NL + KC];   // per warp: strict lower triangle of L (row-major), then 1/d
     __shared__ double log_s[4][K2A_LOG];   // per warp: tau of every step, stepped row in the 7 low mantissa bits
@@ -555,6 +557,7 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
     const double* __restrict__ Gam = P.Gam;
     const double* __restrict__ T0 = P.T0;
     if (max_iter > K2A_LOG) max_iter = K2A_LOG;
+    if (max_iter + max_iter2 > K2A_LOG) max_iter2 = K2A_LOG - max_iter;
     // a key <= ktol proves violation < PPG_FEAS_TOL (keys round down by < 2^-13 relative): time for the exact verification
     const int ktol = (__double2hiint(PPG_FEAS_TOL * 0.999) & ~127) | 127;
     // opaque per-lane constants (kept in registers instead of being rematerialised inside the step loop)
@@ -710,7 +713,15 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
                 for (int r2 = 0; r2 < RPL; ++r2) s[r2] = fma(x[a], K2A_GP(a, lane + r2 * 32), s[r2]);
             }
         };
-        for (int it = 0; it < max_iter; ++it) {
+        // Two phases.  omega = 1.35 minimises the steps of the candidates that converge (scanned 1.2 .. 1.8); the ones that
+        // stall with it (not halving the worst violation in 16 steps: fat sets on which the projections zig-zag) mostly
+        // do converge with a longer stride, so a stall - or the end of the first budget - switches to omega = 1.8 for up to
+        // max_iter2 more steps before the candidate is handed to the simplex (emulated on the CPU first: 4.9 % -> 1.5 %
+        // uncertified for 7 % more steps; omega = 1.8 from the start costs 20 % more steps on everything).
+        double omega = K2A_OMEGA;
+        int it_end = max_iter, chk = 0;
+        bool second = max_iter2 <= 0;   // "already in the last phase"
+        for (int it = 0;; ++it) {
             // arg-max in one 32-bit reduction: the key of a residual is the high word of the double with the row index in
             // its 7 low bits (parked and satisfied rows have negative keys)
             int kmax = 0;
@@ -739,10 +750,21 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
             const double wmax = __hiloint2double(wkey & ~127, 0);   // its violation, rounded down by < 2^-13
             // stall detector: a relaxation that has not halved its worst violation in 16 steps is not going to finish
             // inside the budget (badly scaled or zero-margin sets) -> simplex.  Halving = exponent - 1 = key - 2^20.
-            if ((it & 15) == 0) {
-                if (it != 0 && wkey > wref - 0x100000) break;
+            bool stalled = it >= it_end;
+            if (!stalled && chk == 0) {
+                stalled = it != 0 && wkey > wref - 0x100000;
                 wref = wkey;
+                chk = second ? K2A_STALL2 : 16;
             }
+            if (stalled) {
+                if (second) break;
+                second = true;
+                omega = K2A_OMEGA2;
+                it_end = it + max_iter2;
+                wref = wkey;
+                chk = K2A_STALL2;
+            }
+            --chk;
             double g2[KC];
 #pragma unroll
             for (int a = 0; a < KC; ++a) g2[a] = K2A_GP(a, irow);  // broadcast loads (padded slots: M == 0)
@@ -763,7 +785,7 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
             // z -= tau (g_i - G_A' w).  tau needs no accuracy; its low mantissa bits carry the row
             double rnn;   // gross (20-bit) reciprocal: one MUFU instead of convert - rcp - convert
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rnn) : "d"(nn));
-            const double tau = k2a_key((K2A_OMEGA * wmax) * rnn, irow);
+            const double tau = k2a_key((omega * wmax) * rnn, irow);
             // every lane stores the same word to the same address: no predicate, no branch
             asm volatile("st.shared.f64 [%0], %1;" :: "r"(lg_sa + 8u * (unsigned)nlog), "d"(tau) : "memory");
             ++nlog;
@@ -819,7 +841,8 @@ static cudaError_t launch_k2a_reg(const DevProgram& P, const uint64_t* masks, lo
     const long long need = (n + 127) / 128;   // 32 candidates per warp and queue item
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 128, 0, st>>>(P, masks, n, k_act, status, queue, counters, max_iter);
+    static const int iters2 = getenv("PPGPU_K2A_ITERS2") ? atoi(getenv("PPGPU_K2A_ITERS2")) : 96;
+    kern<<<(unsigned)grid, 128, 0, st>>>(P, masks, n, k_act, status, queue, counters, max_iter, iters2);
     return cudaGetLastError();
 }
 
