@@ -786,8 +786,9 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
             double rnn;   // gross (20-bit) reciprocal: one MUFU instead of convert - rcp - convert
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rnn) : "d"(nn));
             const double tau = k2a_key((omega * wmax) * rnn, irow);
-            // every lane stores the same word to the same address: no predicate, no branch
-            asm volatile("st.shared.f64 [%0], %1;" :: "r"(lg_sa + 8u * (unsigned)nlog), "d"(tau) : "memory");
+            // predicated store by lane 0 (no branch; every lane holds the same tau)
+            asm volatile("{ .reg .pred p; setp.eq.s32 p, %2, 0; @p st.shared.f64 [%0], %1; }"
+                         :: "r"(lg_sa + 8u * (unsigned)nlog), "d"(tau), "r"(lane) : "memory");
             ++nlog;
 #pragma unroll
             for (int rr = 0; rr < RPL; ++rr) v[rr] = fma(-tau, c2[rr], v[rr]);
