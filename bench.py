@@ -245,7 +245,7 @@ def run_gpu(args, rank, world, local_rank):
     value = units * len(ms_dev) / (sum(ms_dev) * 1e-3)
     e2e_value = units * len(ms_e2e) / (sum(ms_e2e) * 1e-3)
     # dominant kernel family of the timed steps and its in-kernel count of useful fp64 FMAs
-    fams = {'k2a_relax': ('k2a_relax_small_kernel (feasibility certificates)', counters['k2a_work'], counters['k2a_tried']),
+    fams = {'k2a_relax': ('k2a_relax_reg_kernel (feasibility certificates)', counters['k2a_work'], counters['k2a_tried']),
             'k2_feas_lp': ('k2_feas_kernel (feasibility simplex)', counters['k2_work'], counters['k2_lps']),
             'k34_kkt_cheb': ('k34_kernel (KKT + Chebyshev screen)', counters['k4_work'], counters['k4_lps'])}
     dom = max(fams, key=lambda f: prof[f]['ms'])

@@ -42,30 +42,69 @@ def table(rows):
     for a, c, b in rows:
         print(f'| {a} | {c} {b} |')
 
+def bench_line(path):
+    try:
+        return json.loads(open(path).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
 print('# Round 1 - measured numbers and ncu evidence (B200, one GPU unless stated)\n')
 print('All captures: `gpurun`, `--clock-control none`, workload = synthetic dense mpQP 100x30x6 '
-      '(`tests/golden/synthetic_30_6_40_s0.npz`), combinatorial levels 1..4 (3,940,375 candidates per step) unless stated. '
-      'Raw reports stay in `gpurun_out/` (scratch); the CSV launch lists are copied here.\n')
-for title, path in (('final version (K2a certificates + simplex for the rest)', 'profiles/r01_launches_final.csv'),
-                    ('v1 (first correct version, simplex for every candidate)', 'profiles/r01_launches_v1.csv')):
+      '(`tests/golden/synthetic_30_6_40_s0.npz`), combinatorial levels 1..5 (74,536,536 candidates per step; the level-5 '
+      'array is evaluated in 18 chunks of 2^22 candidates) unless stated. Raw reports stay in `gpurun_out/` (scratch); the CSV '
+      'launch lists are copied here.\n')
+d = bench_line('gpurun_out/bench_final_l5.json')
+if d:
+    print('## Headline (default `python bench.py`)\n')
+    k = d['kernels_ms_per_step']
+    print(f"{d['value']:.3e} candidates/s device-resident ({d['ms_per_step']:.1f} ms/step), {d['e2e']['value']:.3e} end to end through "
+          f"`solve_mpqp` ({d['e2e']['ms_per_step']:.1f} ms/step), CPU oracle {d['cpu_baseline']['value']:.0f} candidates/s on "
+          f"{d['cpu_baseline']['cores']} cores. Roofline of the dominant kernel family (K2a): {d['roofline']['achieved']:.2f} of "
+          f"{d['roofline']['peak']:.2f} TFLOP/s fp64 = {d['roofline']['frac']:.3f}; share of the step "
+          f"{d['roofline']['share_of_step']:.2f}.\n")
+    print('| kernel family | ms / step (CUDA events inside bench.py) |\n|---|---|')
+    for name, v in sorted(k.items(), key=lambda x: -x[1]):
+        print(f'| {name} | {v:.2f} |')
+    print()
+print('History of the same workload on one B200 (ms per step, levels 1..5): first correct version (simplex for every '
+      'candidate, levels 1..4 only: 674 ms for 3.9e6 candidates) -> K2a v1 certificates 1697 -> K2a v2 in registers 1112 -> '
+      'K2 warm start from the K2a iterate 997 -> block scans of the status bytes in K2/K34 890 -> 32 candidates per K2a '
+      'queue item 853 -> second relaxation phase 748.\n')
+for title, path, cmd in (
+        ('final version, the timed step of the default command', 'profiles/r01_launches_final.csv',
+         '`ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (4th solve of the run = the timed device-resident step)'),
+        ('mid-round version (K2a v1 + simplex for the rest), levels 1..4', 'profiles/r01_launches_k2a_v1.csv',
+         '`... -s <warm-up launches> -c 90 --csv python bench.py --steps 1 --warmup 3 --levels 4 --no-cpu-baseline`'),
+        ('v1 (first correct version, simplex for every candidate), levels 1..4', 'profiles/r01_launches_v1.csv',
+         'same command')):
     agg = launches(path)
     tot = sum(v[1] for v in agg.values())
     print(f'## Launch list of one timed step - {title}\n')
-    print(f'`ncu --metrics gpu__time_duration.sum --clock-control none -s <warm-up launches> -c 90 --csv python bench.py --steps 1 --warmup 3 --levels 4 --no-cpu-baseline` -> `{path}`\n')
+    print(f'{cmd} -> `{path}`\n')
     print('| kernel | launches | ms | share |\n|---|---|---|---|')
-    for k, v in sorted(agg.items(), key=lambda x: -x[1][1])[:10]:
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][1])[:12]:
         print(f'| `{k}` | {v[0]} | {v[1]:.3f} | {100 * v[1] / tot:.1f}% |')
-    print(f'\nTotal {tot:.1f} ms.\n')
-print('## Dominant kernel, final version: `k2a_relax_small_kernel<4,4>` (level-4 launch, 3,776,565 candidates), `ncu --set full`\n')
-table(raw('gpurun_out/r01_k2a_final.ncu-rep', WANT))
-print('\n## v1 dominant kernel `k2_feas_kernel<4,1,40,1>` (same launch, `ncu --set full`)\n')
-table(raw('gpurun_out/r01_k2.ncu-rep', WANT))
-print('\n## Register simplex after the v2-v3 rework `k2_feas_kernel<2,2,40,1>` (all candidates, before K2a existed)\n')
-table(raw('gpurun_out/r01_k2_v4.ncu-rep', WANT))
-for tag, path in (('levels 1..5 (default bench.py, 78,385,935 candidates per step)', 'gpurun_out/bench_final_l5.json'),
-                  ('levels 1..4', 'gpurun_out/bench_final_l4.json'), ('reference arm (`--impl reference`)', 'gpurun_out/bench_ref.json')):
+    print(f'\nTotal {tot:.1f} ms (cold-cache, serialised launches: shares, not absolutes, are comparable with the event timings).\n')
+for title, path in (
+        ('Dominant kernel, final: `k2a_relax_reg_kernel<4,5,true>` (one level-5 chunk, 4,194,304 candidates)', 'gpurun_out/r01_k2a_final_l5.ncu-rep'),
+        ('Final `k2_feas_kernel<2,2,40,1>` (same chunk: warm list + block scan)', 'gpurun_out/r01_k2_final_l5.ncu-rep'),
+        ('Final `k34_kernel<4,8,4>` (same chunk)', 'gpurun_out/r01_k34_final_l5.ncu-rep'),
+        ('K2a v2 before the batched queue: `k2a_relax_reg_kernel<4,4,true>` (level-4 launch, 3,776,565 candidates)', 'gpurun_out/r01_k2a_v2.ncu-rep'),
+        ('K2a v1: `k2a_relax_small_kernel<4,4>` (same level-4 launch)', 'gpurun_out/r01_k2a_final.ncu-rep'),
+        ('v1 dominant kernel `k2_feas_kernel<4,1,40,1>` (level-4 launch, simplex for every candidate)', 'gpurun_out/r01_k2.ncu-rep'),
+        ('Register simplex after the v2-v3 rework `k2_feas_kernel<2,2,40,1>` (all candidates, before K2a existed)', 'gpurun_out/r01_k2_v4.ncu-rep')):
     try:
-        d = json.loads(open(path).read().strip().splitlines()[-1])
+        rows_ = raw(path, WANT)
     except Exception:
+        continue
+    print(f'## {title}, `ncu --set full`\n')
+    table(rows_)
+    print()
+for tag, path in (('levels 1..5 (default bench.py)', 'gpurun_out/bench_final_l5.json'),
+                  ('levels 1..4', 'gpurun_out/bench_final_l4.json'), ('reference arm (`--impl reference`)', 'gpurun_out/bench_ref.json'),
+                  ('2 GPUs', 'gpurun_out/bench_final_2gpu.json'), ('4 GPUs', 'gpurun_out/bench_final_4gpu.json'),
+                  ('8 GPUs', 'gpurun_out/bench_final_8gpu.json')):
+    d = bench_line(path)
+    if d is None:
         continue
     print(f'\n## bench.py line, {tag}\n\n```json\n{json.dumps(d)}\n```')
