@@ -544,7 +544,8 @@ constexpr int K2A_STALL2 = 48;
 template <int RPL, int KC, bool EXACT>
 __global__ void __launch_bounds__(128, (RPL * KC <= 16) ? 5 : ((RPL * KC <= 24) ? 4 : 3))   // 96 registers for 4 x 5 spill M: slower
 k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
-                     unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter, int max_iter2) {
+                     unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter, int max_iter2,
+                     int grab) {
     constexpr int NL = KC * (KC - 1) / 2;
     __shared__ double fac_s[4][NL + KC];   // per warp: strict lower triangle of L (row-major), then 1/d
     __shared__ double log_s[4][K2A_LOG];   // per warp: tau of every step, stepped row in the 7 low mantissa bits
@@ -567,18 +568,19 @@ k2a_relax_reg_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long
 #pragma unroll
     for (int rr = 0; rr < RPL; ++rr) { kid[rr] = rr * 32 + lane; asm volatile("" : "+r"(kid[rr])); }
     unsigned long long n_try = 0, n_ok = 0, n_it = 0;
-    // A warp takes 32 consecutive candidates per queue item: every lane fetches the status byte and the mask words of one of
-    // them up front (the two dependent HBM round trips and the atomic are paid once per 32 candidates, not per candidate),
+    // A warp takes `grab` (<= 32) consecutive candidates per queue item: lanes fetch the status byte and the mask words of one
+    // of them each up front (the two dependent HBM round trips and the atomic are paid once per item, not per candidate),
     // the masks wait in shared memory, and the candidates that need work are then processed one after the other.
+    // The host picks grab = 32 for large launches and less for small ones, so that every warp still sees >= 16 items.
     __shared__ uint64_t mk_s[4][32 * 4];
     for (;;) {
         unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(queue, 32ull);
+        if (lane == 0) q = atomicAdd(queue, (unsigned long long)grab);
         const long long base = (long long)__shfl_sync(PPG_FULL, q, 0);
         if (base >= n) break;
         uint8_t st_l = 0;
         __syncwarp();   // the previous batch's masks are no longer read
-        if (base + lane < n) {
+        if (lane < grab && base + lane < n) {
             st_l = status[base + lane];
             for (int w = 0; w < W; ++w) mk_s[warp][lane * 4 + w] = masks[(base + lane) * W + w];
         }
@@ -839,11 +841,15 @@ static cudaError_t launch_k2a_reg(const DevProgram& P, const uint64_t* masks, lo
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     long long grid = (long long)sm_count * occ;
-    const long long need = (n + 127) / 128;   // 32 candidates per warp and queue item
+    // candidates per warp and queue item: 32 when every warp still gets >= 16 items, fewer for small launches (a warp that
+    // draws one item more than its neighbours is the tail of the launch)
+    int grab = 32;
+    while (grab > 2 && n / grab < 16 * grid * 4) grab >>= 1;
+    const long long need = (n + 4ll * grab - 1) / (4ll * grab);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     static const int iters2 = getenv("PPGPU_K2A_ITERS2") ? atoi(getenv("PPGPU_K2A_ITERS2")) : 96;
-    kern<<<(unsigned)grid, 128, 0, st>>>(P, masks, n, k_act, status, queue, counters, max_iter, iters2);
+    kern<<<(unsigned)grid, 128, 0, st>>>(P, masks, n, k_act, status, queue, counters, max_iter, iters2, grab);
     return cudaGetLastError();
 }
 

@@ -139,7 +139,7 @@ def test_k6_split_between_ranks_equals_single_pass():
         for rank in range(world):
             survive = torch.zeros_like(survive_sum)
             counts = torch.zeros_like(counts_sum)
-            bounds = [(nf * rank // world, nf * (rank + 1) // world)] if nf < 16384 * world else sharding.chunks(nf, rank, world)
+            bounds = [(nf * rank // world, nf * (rank + 1) // world)] if nf < 65536 * world else sharding.chunks(nf, rank, world)
             for lo, hi in bounds:
                 _lib.check(eng.lib.ppgpu_children_count_range(eng.h, feas_masks.data_ptr(), nf, 2, survive.data_ptr(),
                                                               counts.data_ptr(), lo, hi, ws.data_ptr(), ws_bytes,

@@ -106,8 +106,8 @@ def test_chunks_tile_the_level_exactly():
                     seen.append((lo, hi))
             seen.sort()
             assert [x for lo, hi in seen for x in (lo, hi)] == ([0] + [b for _, b in seen[:-1] for b in (b, b)] + [n] if seen else [])
-            if n >= 32 * 16384 * world and world > 1:
-                assert all(len(chunks(n, r, world)) == 32 for r in range(world))
+            if n >= 16 * 65536 * world and world > 1:
+                assert all(len(chunks(n, r, world)) == 16 for r in range(world))
 
 
 WORKER = r'''
