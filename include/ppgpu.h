@@ -70,7 +70,9 @@ int ppgpu_root_level(ppgpu_program* prog, uint64_t* d_masks, int64_t* h_count, p
  * K1 rank screen (is_full_rank, constraint_utilities.py:222-236), K2 feasibility LP (mplp_program.py:411-444),
  * K3/K4 optimality + full-dimension screen (mpqp_program.py:203-322, mpqp_utils.py:323-344).
  * Writes one status byte per candidate (PPG_ST_* bits of csrc/tolerances.h).  stages: bit0 K1, bit1 K2 (preceded by the
- * K2a relaxation certificates unless bit3 is set), bit2 K3/K4. */
+ * K2a relaxation certificates unless bit3 is set), bit2 K3/K4.  Asynchronous on `stream`; large n is processed in chunks
+ * internally (PPGPU_CHUNK candidates), the library owns the K2a -> K2 hand-over scratch (grown on demand, pooled across
+ * handles); d_masks / d_status may be arbitrary sub-ranges of a level (that is how a level is sharded between GPUs). */
 int ppgpu_level_eval(ppgpu_program* prog, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
                      int32_t stages, ppgpu_stream stream);
 

@@ -10,10 +10,12 @@
 // All inner products come from the candidate-independent Gram matrix  Gam = G G'  (R0 x R0, built once per program):
 //     residuals:  v <- v - tau * ( Gam[:,i] - Gam[:,A] w ),   w = (Gam[A,A])^-1 Gam[A,i]        (R0 x (1 + k') FMAs)
 // i.e. ~8x less arithmetic per step than a simplex pivot, 40 registers per thread instead of 250, no block barrier.
-// When the largest violation drops below PPG_FEAS_TOL the point is re-verified EXACTLY (v = G z - h recomputed from z,
+// When the largest violation drops below PPG_FEAS_TOL the point is re-verified EXACTLY (every residual G z - h recomputed,
 // equality residuals included) and only then is PPG_ST_FEAS set - the same acceptance rule as the LP (s* >= -1e-7).
-// Candidates that do not converge within `max_iter` steps (all infeasible ones, and thin/degenerate feasible sets) are
-// left untouched for K2.  The relaxation never decides infeasibility.
+// Candidates that do not converge within the step budget (all infeasible ones, and sets on which the projections
+// zig-zag) are left for K2 - the register-resident kernel hands K2 the exact residuals of its last iterate, so the
+// simplex starts from there (DevProgram::warm_*).  The relaxation never decides infeasibility.
+// Two kernels: k2a_relax_reg_kernel (k' <= 8, R0 <= 128: the production path) and the generic k2a_relax_kernel.
 #include "common.cuh"
 #include "launch.h"
 #include "lp_core.cuh"
@@ -23,7 +25,6 @@
 namespace ppgpu {
 
 __device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }  // no NaN fix-up (fmax costs ~10 SASS)
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 constexpr double K2A_OMEGA = 1.35;  // scanned 1.2 .. 1.8 on the 100x30x6 program: fewest steps (32 vs 39 at 1.5)
 
@@ -242,270 +243,8 @@ static cudaError_t launch_k2a_t(const DevProgram& P, const uint64_t* masks, long
 }
 
 
-// Register-cached variant for small active sets (k' <= KC): M = Gam[:,A] * Sinv (R0 x k') lives in registers, so a step
-// touches ONE row of Gam (coalesced) and k' broadcast words of shared memory; the point itself is carried as
-// coefficients c (z = sum_r c_r g_r) and only materialised for the exact verification.
-template <int RPL, int KC>
-__global__ void __launch_bounds__(128, (RPL * KC <= 16) ? 5 : ((RPL * KC <= 24) ? 4 : 3))
-k2a_relax_small_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
-                       unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int max_iter) {
-    extern __shared__ double dyn_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int R0 = P.R0, nf = P.nfree, dc0 = P.dc0, W = P.W, k = k_act;
-    // per-warp scratch: Sinv (KC x KC), ga (KC), cs (R0), zs (nf), act (KC ints), touched rows (R0 ints)
-    const size_t per_warp = (size_t)KC * KC + KC + (size_t)R0 + (size_t)nf + (size_t)(KC / 2 + 1) + (size_t)(R0 / 2 + 1);
-    double* Sinv = dyn_smem + per_warp * warp;
-    double* ga = Sinv + KC * KC;
-    double* cs = ga + KC;
-    double* zs = cs + R0;
-    int* act = reinterpret_cast<int*>(zs + nf);
-    int* touched = act + 2 * (KC / 2 + 1);
-    const double* __restrict__ Gam = P.Gam;
-    const double* __restrict__ T0 = P.T0;
-    unsigned long long n_try = 0, n_ok = 0, n_it = 0;
-    for (;;) {
-        unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(queue, 1ull);
-        const long long idx = (long long)__shfl_sync(PPG_FULL, q, 0);
-        if (idx >= n) break;
-        const uint8_t st = status[idx];
-        if (!(st & PPG_ST_RANK) || (st & PPG_ST_FEAS)) continue;
-        const uint64_t* mk = masks + idx * W;
-        ++n_try;
-        __syncwarp();
-        if (lane < k) act[lane] = mask_nth(mk, W, lane);
-        __syncwarp();
-        // ---- S = Gam[A,A] -> Cholesky -> Sinv; lane c owns column c
-        if (lane < KC * KC) {
-            const int a = lane / KC, b = lane % KC;
-            Sinv[lane] = (a < k && b < k) ? __ldg(Gam + (size_t)act[a] * R0 + act[b]) : (a == b ? 1.0 : 0.0);
-        }
-        if (KC * KC > 32 && lane + 32 < KC * KC) {
-            const int e = lane + 32, a = e / KC, b = e % KC;
-            Sinv[e] = (a < k && b < k) ? __ldg(Gam + (size_t)act[a] * R0 + act[b]) : (a == b ? 1.0 : 0.0);
-        }
-        __syncwarp();
-        bool pd = true;
-        {
-            // Cholesky in shared memory (lanes over rows), then lane c solves L L' x = e_c for column c of the inverse
-            for (int j = 0; j < KC; ++j) {
-                const double d = Sinv[j * KC + j];
-                if (!(d > 1e-300)) { pd = false; break; }
-                const double sd = sqrt(d);
-                __syncwarp();
-                if (lane > j && lane < KC) Sinv[lane * KC + j] /= sd;
-                if (lane == 0) Sinv[j * KC + j] = sd;
-                __syncwarp();
-                if (lane > j && lane < KC) {
-                    const double lij = Sinv[lane * KC + j];
-                    for (int c = j + 1; c <= lane; ++c) Sinv[lane * KC + c] = fma(-lij, Sinv[c * KC + j], Sinv[lane * KC + c]);
-                }
-                __syncwarp();
-            }
-            double x[KC];
-            if (pd && lane < KC) {
-#pragma unroll
-                for (int i = 0; i < KC; ++i) {
-                    double s2 = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int j = 0; j < KC; ++j) if (j < i) s2 = fma(-Sinv[i * KC + j], x[j], s2);
-                    x[i] = s2 / Sinv[i * KC + i];
-                }
-#pragma unroll
-                for (int i = KC - 1; i >= 0; --i) {
-                    double s2 = x[i];
-#pragma unroll
-                    for (int j = 0; j < KC; ++j) if (j > i) s2 = fma(-Sinv[j * KC + i], x[j], s2);
-                    x[i] = s2 / Sinv[i * KC + i];
-                }
-            }
-            __syncwarp();
-            if (pd && lane < KC) {
-#pragma unroll
-                for (int i = 0; i < KC; ++i) Sinv[i * KC + lane] = x[i];
-            }
-            __syncwarp();
-        }
-        if (!__all_sync(PPG_FULL, pd)) continue;
-        // ---- per-lane constants: rows of Gam[A,:] folded with Sinv, start residuals, start coefficients.
-        // Addressing is hoisted out of the step loop (v1 of this kernel spent 2/3 of its instructions on 64-bit index
-        // arithmetic and bounds predicates): row pointers of the active rows, clamped row index per lane slot, and
-        // padded active slots that point at a valid row but carry M == 0.
-        double M[RPL][KC], v[RPL];
-        bool isA[RPL], use[RPL];
-        unsigned growA[KC];   // element offsets of the active rows of Gam (32-bit: base pointer stays uniform)
-#pragma unroll
-        for (int a = 0; a < KC; ++a) growA[a] = (unsigned)act[a < k ? a : 0] * (unsigned)R0;
-        int rcl[RPL];
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr) rcl[rr] = min(rr * 32 + lane, R0 - 1);
-        double cA = 0.0;  // coefficient of active row `lane` (lanes < k); inequality coefficients live in cs[]
-        int ntouched = 0; // distinct rows stepped on so far (their ids are in touched[])
-        double srow[KC];  // row `lane` of Sinv (lanes < KC)
-#pragma unroll
-        for (int b2 = 0; b2 < KC; ++b2) srow[b2] = Sinv[(lane < KC ? lane : 0) * KC + b2];
-        {
-            double w0[KC];
-#pragma unroll
-            for (int a = 0; a < KC; ++a) {
-                double s2 = 0.0;
-#pragma unroll
-                for (int b = 0; b < KC; ++b) s2 = fma(Sinv[a * KC + b], (b < k) ? __ldg(T0 + (size_t)act[b] * dc0) : 0.0, s2);
-                w0[a] = (a < k) ? s2 : 0.0;
-                if (a == lane) cA = w0[a];
-            }
-#pragma unroll
-            for (int rr = 0; rr < RPL; ++rr) {
-                const int r = rr * 32 + lane;
-                double gA[KC];
-#pragma unroll
-                for (int a = 0; a < KC; ++a) gA[a] = (a < k) ? __ldg(Gam + (growA[a] + (unsigned)rcl[rr])) : 0.0;
-                double s2 = -__ldg(T0 + (size_t)rcl[rr] * dc0);
-#pragma unroll
-                for (int a = 0; a < KC; ++a) {
-                    double m2 = 0.0;
-#pragma unroll
-                    for (int b = 0; b < KC; ++b) m2 = fma(gA[b], Sinv[b * KC + a], m2);
-                    M[rr][a] = (a < k) ? m2 : 0.0;
-                    s2 = fma(gA[a], w0[a], s2);
-                }
-                isA[rr] = r < P.mi && mask_test(mk, r);
-                use[rr] = r < R0 && !isA[rr];
-                v[rr] = use[rr] ? s2 : -1e300;   // parked: never the maximum, never updated meaningfully
-                if (r < R0) cs[r] = 0.0;
-            }
-        }
-        __syncwarp();
-        bool feasible = false;
-        int rechecks = 0;
-        double wref = 0.0;
-        for (int it = 0; it < max_iter; ++it) {
-            double lv = 0.0;
-#pragma unroll
-            for (int rr = 0; rr < RPL; ++rr) lv = dmax2(lv, v[rr]);
-            const double wmax = warp_max_nonneg(lv);
-            if (wmax <= PPG_FEAS_TOL) {
-                // ---- exact verification: materialise z from the coefficients, recompute every near-binding row
-                __syncwarp();
-                if (lane < k) cs[act[lane]] = cA;
-                __syncwarp();
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = cc * 32 + lane;
-                    if (c < nf) {
-                        double s2 = 0.0;
-                        for (int a2 = 0; a2 < k; ++a2) s2 = fma(cs[act[a2]], __ldg(T0 + (size_t)act[a2] * dc0 + 1 + c), s2);
-                        for (int j2 = 0; j2 < ntouched; ++j2) {
-                            const int r = touched[j2];
-                            s2 = fma(cs[r], __ldg(T0 + (size_t)r * dc0 + 1 + c), s2);
-                        }
-                        zs[c] = s2;
-                    }
-                }
-                __syncwarp();
-                double worst = 0.0;
-#pragma unroll
-                for (int rr = 0; rr < RPL; ++rr) {
-                    const int r = rr * 32 + lane;
-                    if (r < R0 && (isA[rr] || v[rr] > -1e-3)) {  // (parked rows hold -1e300: only isA brings them in)  // far-from-binding rows cannot be off by 1e-3 (error <= ~1e-7)
-                        const double* g = T0 + (size_t)r * dc0;
-                        double s2 = -__ldg(g);
-                        for (int c = 0; c < nf; ++c) s2 = fma(__ldg(g + 1 + c), zs[c], s2);
-                        v[rr] = isA[rr] ? -1e300 : s2;
-                        worst = dmax2(worst, isA[rr] ? fabs(s2) : s2);
-                    }
-                }
-                worst = warp_max_nonneg(dmax2(worst, 0.0));
-                if (worst <= PPG_FEAS_TOL) { feasible = true; break; }
-                if (++rechecks > 3) break;
-                if (lane < k) cs[act[lane]] = 0.0;  // active-row slots of cs are only borrowed for the verification
-                __syncwarp();
-                continue;
-            }
-            int myslot = -1;
-#pragma unroll
-            for (int rr = RPL - 1; rr >= 0; --rr) if (v[rr] == wmax) myslot = rr;
-            const int wl = __ffs((int)__ballot_sync(PPG_FULL, myslot >= 0)) - 1;   // any most-violated row will do
-            const int wslot = __shfl_sync(PPG_FULL, myslot, wl);
-            const int irow = wslot * 32 + wl;
-            // stall detector: a relaxation that has not halved its worst violation in 16 steps is not going to finish
-            // inside the budget (badly scaled or zero-margin sets; 0 of 1147 converging probes tripped it) -> simplex
-            if ((it & 15) == 0) {
-                if (it != 0 && wmax > 0.5 * wref) break;
-                wref = wmax;
-            }
-            ++n_it;
-            double g2[KC];
-#pragma unroll
-            for (int a = 0; a < KC; ++a) g2[a] = __ldg(Gam + (growA[a] + (unsigned)irow));  // broadcast loads (padded slots: M == 0)
-            const unsigned gi = (unsigned)irow * (unsigned)R0;
-            double c2[RPL];
-            double mycol = 0.0;
-#pragma unroll
-            for (int rr = 0; rr < RPL; ++rr) {
-                double x2 = __ldg(Gam + (gi + (unsigned)rcl[rr]));
-#pragma unroll
-                for (int a = 0; a < KC; ++a) x2 = fma(-M[rr][a], g2[a], x2);
-                c2[rr] = x2;
-                if (rr == wslot) mycol = x2;
-            }
-            const double nn = shfl_d(mycol, wl);   // |N g_i|^2
-            if (!(nn > 1e-12)) break;                      // row i lies in the span of the active rows: leave it to the LP
-            // the relaxation parameter needs no accuracy: fp32 reciprocal
-            const double tau = (K2A_OMEGA * wmax) * (double)rcp_approx((float)nn);
-#pragma unroll
-            for (int rr = 0; rr < RPL; ++rr) v[rr] = fma(-tau, c2[rr], v[rr]);
-            // z -= tau (g_i - G_A' w),  w = Sinv ga: lane a accumulates the coefficient of its active row
-            {
-                const double old = cs[irow];      // broadcast read; the row list only grows on a first visit
-                __syncwarp();
-                if (lane == 0) {
-                    if (old == 0.0) touched[ntouched] = irow;
-                    cs[irow] = old - tau;
-                }
-                if (old == 0.0) ++ntouched;
-                double wa = 0.0;
-#pragma unroll
-                for (int b2 = 0; b2 < KC; ++b2) wa = fma(srow[b2], g2[b2], wa);
-                if (lane < k) cA = fma(tau, wa, cA);
-            }
-            __syncwarp();  // lane 0's update of cs / touched must be visible to the next step's broadcast read
-        }
-        if (feasible) {
-            ++n_ok;
-            if (lane == 0) status[idx] = st | PPG_ST_FEAS;
-        }
-    }
-    if (lane == 0 && n_try) {
-        atomicAdd(&counters[CNT_K2A_TRIED], n_try);
-        atomicAdd(&counters[CNT_K2A_CERTIFIED], n_ok);
-        atomicAdd(&counters[CNT_K2A_STEPS], n_it);
-        atomicAdd(&counters[CNT_K2A_WORK], n_it * (unsigned long long)(R0 * (k + 1)));
-    }
-}
-
-template <int RPL, int KC>
-static cudaError_t launch_k2a_small(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
-                                    unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count,
-                                    cudaStream_t st) {
-    auto kern = k2a_relax_small_kernel<RPL, KC>;
-    const size_t per_warp = (size_t)KC * KC + KC + (size_t)P.R0 + (size_t)P.nfree + (size_t)(KC / 2 + 1) + (size_t)(P.R0 / 2 + 1);
-    const size_t smem = per_warp * 4 * sizeof(double);
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
-    long long grid = (long long)sm_count * occ;
-    const long long need = (n + 3) / 4;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 128, smem, st>>>(P, masks, n, k_act, status, queue, counters, max_iter);
-    return cudaGetLastError();
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------------
-// v2 of the register-cached variant: everything candidate-specific lives in registers.
+// Register-resident variant for small active sets (k' <= 8, R0 <= 128): everything candidate-specific lives in registers.
 //   * Gam[A,A] is factorised as L D L' by every lane redundantly (k' <= 8: ~60 FMAs, no shared memory, no __syncwarp,
 //     no sqrt and k' reciprocals instead of 3k' divisions), M's rows are triangular solves against it;
 //   * the point is carried as the log of its steps (tau_e, row i_e): z = -sum_e tau_e g_{i_e} + G_A' x - one shared
@@ -866,27 +605,16 @@ static cudaError_t launch_k2a_reg_k(const DevProgram& P, const uint64_t* masks, 
 #undef K2A_REG
 }
 
-#define K2A_SMALL(KCV)                                                                                                   \
-    if (P.R0 <= 32) return launch_k2a_small<1, KCV>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);  \
-    if (P.R0 <= 64) return launch_k2a_small<2, KCV>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);  \
-    if (P.R0 <= 128) return launch_k2a_small<4, KCV>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
-
 cudaError_t launch_k2a(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count, cudaStream_t st) {
     if (k_act > 32 || P.nfree > 64) return cudaSuccess;  // outside the certificate kernel's envelope: K2 decides alone
-    static const int variant = getenv("PPGPU_K2A_V") ? atoi(getenv("PPGPU_K2A_V")) : 2;
-    if (variant == 2 && k_act >= 1 && k_act <= 8 && P.R0 <= 128) {
+    if (k_act >= 1 && k_act <= 8 && P.R0 <= 128) {
         if (k_act <= 3) return launch_k2a_reg_k<3>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
         if (k_act == 4) return launch_k2a_reg_k<4>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
         if (k_act == 5) return launch_k2a_reg_k<5>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
         if (k_act == 6) return launch_k2a_reg_k<6>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
         return launch_k2a_reg_k<8>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
     }
-    if (k_act >= 1 && k_act <= 3 && P.R0 <= 128) { K2A_SMALL(3) }
-    if (k_act == 4 && P.R0 <= 128) { K2A_SMALL(4) }
-    if (k_act == 5 && P.R0 <= 128) { K2A_SMALL(5) }
-    if (k_act == 6 && P.R0 <= 128) { K2A_SMALL(6) }
-    if (k_act >= 7 && k_act <= 8 && P.R0 <= 128) { K2A_SMALL(8) }
     if (P.R0 <= 32) return launch_k2a_t<1>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
     if (P.R0 <= 64) return launch_k2a_t<2>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
     if (P.R0 <= 128) return launch_k2a_t<4>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
