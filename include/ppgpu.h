@@ -111,6 +111,25 @@ int ppgpu_children_scan(ppgpu_program* prog, int64_t* d_counts_to_offsets, int64
 int ppgpu_children_write(ppgpu_program* prog, const uint64_t* d_feas_masks, const uint64_t* d_survive,
                          const int64_t* d_offsets, int64_t nf, uint64_t* d_children, ppgpu_stream stream);
 
+/* Batched point location + law evaluation for a solved program (Solution.get_region / evaluate, solution.py:44-112 with
+ * region.is_inside, critical_region.py:81-84;  upop.PointLocation.locate / evaluate, upop/point_location.py:43-133).
+ * Stateless - no program handle.
+ *   d_theta   n_points x t                    parameter points
+ *   d_rows    total_rows x (t + 1)            stacked half-spaces [f | E] of all regions, solution order
+ *   d_row_off n_regions + 1                   first row of every region
+ *   d_laws    n_regions x n_x x (t + 1)       [b | A] of every region (may be NULL when d_x is NULL and overlap is 0)
+ *   use_tol   1: inside iff all(E theta - f < tol)   (Solution, tol = point_location_tolerance)
+ *             0: inside iff all(E theta <= f)        (upop.PointLocation)
+ *   overlap   0: the FIRST containing region (get_region_no_overlap)
+ *             1: the containing region with the lowest objective 1/2 x'Qx + theta'H'x + c'x, ties to the later one
+ *                (get_region_overlap); needs d_H (n_x x t), d_c (n_x) and, for an mpQP, d_Q (n_x x n_x, else NULL)
+ *   d_region  n_points int32                  index of that region, -1 if none
+ *   d_x       n_points x n_x or NULL          A theta + b of that region, NaN where d_region is -1 */
+int ppgpu_locate_points(const double* d_theta, int64_t n_points, int32_t t, const double* d_rows, const int64_t* d_row_off,
+                        int64_t n_regions, const double* d_laws, int32_t n_x, int32_t use_tol, double tol, int32_t overlap,
+                        const double* d_Q, const double* d_H, const double* d_c, int32_t* d_region, double* d_x,
+                        ppgpu_stream stream);
+
 /* cumulative device counters (LPs, pivots, useful FMAs per kernel family, borderline/numeric flags) */
 int ppgpu_counters(ppgpu_program* prog, uint64_t* h_out, int32_t reset, ppgpu_stream stream);
 

@@ -7,6 +7,7 @@
 """
 from .mp_solvers.solve_mpqp import mpqp_algorithm, solve_mpqp  # noqa: F401
 from .mplp_program import MPLP_Program, MPQP_Program  # noqa: F401
+from .point_location import PointLocation  # noqa: F401
 
 
 def install(ppopt_package=None):

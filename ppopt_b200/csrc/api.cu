@@ -455,6 +455,27 @@ int ppgpu_profile_read(ppgpu_program* p, double* h_ms, int64_t* h_launches, int3
     return 0;
 }
 
+int ppgpu_locate_points(const double* d_theta, int64_t n_points, int32_t t, const double* d_rows, const int64_t* d_row_off,
+                        int64_t n_regions, const double* d_laws, int32_t n_x, int32_t use_tol, double tol, int32_t overlap,
+                        const double* d_Q, const double* d_H, const double* d_c, int32_t* d_region, double* d_x,
+                        ppgpu_stream stream) {
+    if (n_points < 0 || n_regions < 0 || n_x < 0) return fail_msg("negative size");
+    if (n_points == 0) return 0;
+    if (!d_theta || !d_region || !d_row_off || (n_regions > 0 && !d_rows)) return fail_msg("null argument");
+    if ((d_x || overlap) && n_x > 0 && n_regions > 0 && !d_laws) return fail_msg("laws needed (d_x or overlap) but d_laws is NULL");
+    if (t < 1 || t > 32) return fail_msg("point location supports 1 <= t <= 32 parameters");
+    if (overlap && (n_x < 1 || n_x > 128)) return fail_msg("the overlapping rule supports 1 <= n_x <= 128 variables");
+    if (overlap && (!d_H || !d_c)) return fail_msg("the overlapping rule needs the objective (d_H, d_c; d_Q for an mpQP)");
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail("device query", e);
+    e = launch_locate(d_theta, n_points, t, d_rows, (const long long*)d_row_off, n_regions, d_laws, n_x, use_tol, tol,
+                      overlap ? 1 : 0, d_Q, d_H, d_c, d_region, d_x, sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("K7 point location", e);
+    return 0;
+}
+
 int ppgpu_measure_fp64_peak(int32_t iters, double* h_tflops, ppgpu_stream stream) {
     if (!h_tflops) return fail_msg("null argument");
     cudaError_t e = measure_fp64_peak(iters, h_tflops, (cudaStream_t)stream);

@@ -40,6 +40,11 @@ cudaError_t children_scan(long long* counts_to_offsets, long long nf, void* ws, 
 cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, const uint64_t* survive,
                            const long long* offsets, long long nf, uint64_t* children, cudaStream_t st);
 
+cudaError_t launch_locate(const double* theta, long long n_points, int t, const double* rows, const long long* row_off,
+                          long long n_regions, const double* laws, int n_x, int use_tol, double tol, int overlap,
+                          const double* Qm, const double* Hm, const double* cv, int* region_out, double* x_out, int sm_count,
+                          cudaStream_t st);
+
 cudaError_t launch_clear_bits(uint8_t* status, long long n, uint8_t bits, cudaStream_t st);
 
 cudaError_t measure_fp64_peak(int iters, double* tflops, cudaStream_t st);
