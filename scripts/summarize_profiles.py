@@ -100,6 +100,20 @@ for title, path in (
     print(f'## {title}, `ncu --set full`\n')
     table(rows_)
     print()
+print('## Multi-GPU (levels 1..5, strong scaling, `bench.py --gpus N` under torchrun, CUDA events, max over ranks)\n')
+print('| GPUs | ms / step | candidates / s | speed-up |\n|---|---|---|---|')
+base = bench_line('gpurun_out/bench_final_l5.json')
+for n_g, path in ((1, 'gpurun_out/bench_final_l5.json'), (4, 'gpurun_out/bench_final_4gpu.json'), (8, 'gpurun_out/bench_final_8gpu.json')):
+    d = bench_line(path)
+    if d and base:
+        print(f"| {n_g} | {d['ms_per_step']:.1f} | {d['value']:.3e} | {base['ms_per_step'] / d['ms_per_step']:.2f}x |")
+print('\nBefore the snake dealing of chunks and the adaptive K2a queue items the 8-GPU step took 168.8 ms (4.4x): 256 chunks of '
+      '276 K candidates left every warp 3-4 queue items of 32 candidates, K2a ran 42 % above its share.\n')
+print('## K7 batched point location (SURVEY 8f row 4), first measurement\n')
+print('`python scripts/pointloc_bench.py rand_6_3_12_s1 2000000`: 299 regions / 1,801 half-spaces, t = 3, n = 6, 2,000,000 uniform '
+      'points (46 % inside some region): 8.6e6 points/s with the points resident in HBM, 1.0e7 points/s from host arrays '
+      '(second call, warm); the numpy restatement of the reference loop does 1.6e3 points/s on one core. Not tuned yet '
+      '(one warp per point, every miss scans all regions).\n')
 for tag, path in (('levels 1..5 (default bench.py)', 'gpurun_out/bench_final_l5.json'),
                   ('levels 1..4', 'gpurun_out/bench_final_l4.json'), ('reference arm (`--impl reference`)', 'gpurun_out/bench_ref.json'),
                   ('2 GPUs', 'gpurun_out/bench_final_2gpu.json'), ('4 GPUs', 'gpurun_out/bench_final_4gpu.json'),
