@@ -467,6 +467,123 @@ int emit_region(Twin& tw, const std::vector<int>& act, double* laws_out, double*
     return 1;
 }
 
+
+// ---- K2a: sequential statement of k2a_relax_reg_kernel (ppopt_b200/csrc/k2a_relax.cu) -------------------------------
+// Same algorithm and constants (LDL' of Gam[A,A], residual recursion through M = Gam[:,A] S^-1, 32-bit arg-max keys, the two
+// relaxation phases with their stall detectors, step log, exact verification in Gram space).  The step length uses an
+// exact reciprocal where the kernel uses MUFU.RCP64H, so step COUNTS may differ by a few; what the CPU tests pin is the
+// property the product relies on: a certified candidate is feasible, and the residuals handed to the simplex are exact.
+struct K2aOut { int certified; int steps; std::vector<double> resid; };
+
+static inline int hi_word(double v) { int64_t b; std::memcpy(&b, &v, 8); return (int)(b >> 32); }
+static inline double from_hi(int hi) { int64_t b = (int64_t)(uint32_t)hi << 32; double v; std::memcpy(&v, &b, 8); return v; }
+
+K2aOut k2a_certify(const ReducedProgram& P, const std::vector<int>& act, int max_iter, int max_iter2) {
+    const int R0 = P.R0, k = (int)act.size(), dc = P.nfree + 2;
+    K2aOut out{0, 0, {}};
+    auto G = [&](int i, int j) { return P.Gam[(size_t)i * R0 + j]; };
+    auto h = [&](int r) { return P.T0[(size_t)r * dc]; };
+    // S = L D L'
+    std::vector<double> L((size_t)k * k, 0.0), dd(k), dinv(k);
+    for (int i = 0; i < k; ++i) for (int j = 0; j <= i; ++j) { if (i == j) dd[i] = G(act[i], act[j]); else L[(size_t)i * k + j] = G(act[i], act[j]); }
+    for (int j = 0; j < k; ++j) {
+        std::vector<double> wj(k, 0.0);
+        for (int c = 0; c < j; ++c) { wj[c] = L[(size_t)j * k + c] * dd[c]; dd[j] = std::fma(-L[(size_t)j * k + c], wj[c], dd[j]); }
+        if (!(dd[j] > 1e-300)) return out;
+        dinv[j] = 1.0 / dd[j];
+        for (int i = j + 1; i < k; ++i) {
+            double e = L[(size_t)i * k + j];
+            for (int c = 0; c < j; ++c) e = std::fma(-L[(size_t)i * k + c], wj[c], e);
+            L[(size_t)i * k + j] = e * dinv[j];
+        }
+    }
+    auto solve = [&](std::vector<double>& x) {
+        for (int i = 1; i < k; ++i) for (int c = 0; c < i; ++c) x[i] = std::fma(-L[(size_t)i * k + c], x[c], x[i]);
+        for (int i = 0; i < k; ++i) x[i] *= dinv[i];
+        for (int i = k - 2; i >= 0; --i) for (int c = i + 1; c < k; ++c) x[i] = std::fma(-L[(size_t)c * k + i], x[c], x[i]);
+    };
+    std::vector<double> w0(k);
+    for (int a = 0; a < k; ++a) w0[a] = h(act[a]);
+    solve(w0);
+    std::vector<char> isa(R0, 0);
+    for (int a : act) isa[a] = 1;
+    std::vector<double> M((size_t)R0 * k), v(R0);
+    for (int r = 0; r < R0; ++r) {
+        std::vector<double> x(k);
+        double s2 = -h(r);
+        for (int a = 0; a < k; ++a) { x[a] = G(act[a], r); s2 = std::fma(x[a], w0[a], s2); }
+        solve(x);
+        for (int a = 0; a < k; ++a) M[(size_t)r * k + a] = x[a];
+        v[r] = isa[r] ? -1e300 : s2;
+    }
+    std::vector<double> log_tau;
+    std::vector<int> log_row;
+    auto exact = [&](std::vector<double>& s) {
+        s.assign(R0, 0.0);
+        std::vector<double> t(k, 0.0);
+        for (int r = 0; r < R0; ++r) s[r] = -h(r);
+        for (size_t e = 0; e < log_tau.size(); ++e) {
+            for (int r = 0; r < R0; ++r) s[r] = std::fma(-log_tau[e], G(log_row[e], r), s[r]);
+            for (int a = 0; a < k; ++a) t[a] = std::fma(-log_tau[e], G(log_row[e], act[a]), t[a]);
+        }
+        std::vector<double> x(k);
+        for (int a = 0; a < k; ++a) x[a] = h(act[a]) - t[a];
+        solve(x);
+        for (int a = 0; a < k; ++a) for (int r = 0; r < R0; ++r) s[r] = std::fma(x[a], G(act[a], r), s[r]);
+    };
+    const int ktol = (hi_word(PPG_FEAS_TOL * 0.999) & ~127) | 127;
+    if (max_iter > 192) max_iter = 192;
+    if (max_iter + max_iter2 > 192) max_iter2 = 192 - max_iter;
+    double omega = 1.35;
+    int it_end = max_iter, chk = 0, rechecks = 0, wref = 0;
+    bool second = max_iter2 <= 0, feasible = false;
+    std::vector<double> s;
+    for (int it = 0;; ++it) {
+        int wkey = 0;
+        for (int r = 0; r < R0; ++r) wkey = std::max(wkey, (hi_word(v[r]) & ~127) | r);
+        if (wkey <= ktol) {
+            exact(s);
+            double worst = 0.0;
+            for (int r = 0; r < R0; ++r) {
+                worst = std::fmax(worst, isa[r] ? std::fabs(s[r]) : s[r]);
+                v[r] = isa[r] ? -1e300 : s[r];
+            }
+            if (worst <= PPG_FEAS_TOL) { feasible = true; break; }
+            if (++rechecks > 3) break;
+            continue;
+        }
+        const int irow = wkey & 127;
+        const double wmax = from_hi(wkey & ~127);
+        bool stalled = it >= it_end;
+        if (!stalled && chk == 0) {
+            stalled = it != 0 && wkey > wref - 0x100000;
+            wref = wkey;
+            chk = second ? 48 : 16;
+        }
+        if (stalled) {
+            if (second) break;
+            second = true; omega = 1.8; it_end = it + max_iter2; wref = wkey; chk = 48;
+        }
+        --chk;
+        std::vector<double> g2(k), c2(R0);
+        for (int a = 0; a < k; ++a) g2[a] = G(act[a], irow);
+        for (int r = 0; r < R0; ++r) {
+            double x2 = G(irow, r);
+            for (int a = 0; a < k; ++a) x2 = std::fma(-M[(size_t)r * k + a], g2[a], x2);
+            c2[r] = x2;
+        }
+        const double nn = c2[irow];
+        if (!(nn > 1e-12)) break;
+        const double tau = (omega * wmax) * (1.0 / nn);
+        log_tau.push_back(tau); log_row.push_back(irow);
+        for (int r = 0; r < R0; ++r) v[r] = std::fma(-tau, c2[r], v[r]);
+    }
+    out.certified = feasible ? 1 : 0;
+    out.steps = (int)log_tau.size();
+    if (!feasible) { exact(s); out.resid = s; }
+    return out;
+}
+
 }  // namespace
 
 extern "C" {
@@ -549,6 +666,22 @@ int twin_nfree(void* h) { return ((Twin*)h)->P.nfree; }
 void twin_t0(void* h, double* out) {
     const ReducedProgram& P = ((Twin*)h)->P;
     for (size_t i = 0; i < P.T0.size(); ++i) out[i] = P.T0[i];
+}
+
+// K2a restatement for n candidates: flags[i] = 1 certified feasible / 0 not; steps[i]; for uncertified candidates the exact
+// residuals G z* - h of the last iterate (what the kernel hands to K2) go to resid[i * R0 ..], zeros otherwise
+void twin_k2a(void* h, const uint64_t* masks, long ncand, int max_iter, int max_iter2, int32_t* flags, int32_t* steps,
+              double* resid) {
+    Twin& tw = *(Twin*)h;
+    const ReducedProgram& P = tw.P;
+    std::vector<int> act;
+    for (long ci = 0; ci < ncand; ++ci) {
+        active_list(P, masks + ci * P.W, act);
+        K2aOut o = k2a_certify(P, act, max_iter, max_iter2);
+        flags[ci] = o.certified;
+        steps[ci] = o.steps;
+        if (resid) for (int r = 0; r < P.R0; ++r) resid[(size_t)ci * P.R0 + r] = o.resid.empty() ? 0.0 : o.resid[r];
+    }
 }
 
 int twin_emit(void* h, const uint64_t* mask, double* laws_out, double* rows_out, int32_t* flags_out, double* info) {

@@ -26,6 +26,8 @@ def lib():
         l.twin_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         l.twin_emit.argtypes = [ctypes.c_void_p] * 6
         l.twin_emit_margins.argtypes = [ctypes.c_void_p] * 7
+        l.twin_k2a.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+        l.twin_feas_rhs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _lib = l
     return _lib
 
@@ -84,6 +86,25 @@ class Twin:
             return rc, laws, rows, flags, info, mg
         rc = lib().twin_emit(self.h, mask.ctypes.data, laws.ctypes.data, rows.ctypes.data, flags.ctypes.data, info.ctypes.data)
         return rc, laws, rows, flags, info
+
+    def k2a(self, masks, max_iter=96, max_iter2=96):
+        """sequential K2a (relaxation certificates): (certified flags, steps, exact residuals of the uncertified ones)"""
+        masks = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(-1, self.W)
+        n = masks.shape[0]
+        flags, steps = numpy.zeros(n, dtype=numpy.int32), numpy.zeros(n, dtype=numpy.int32)
+        resid = numpy.zeros((n, self.R0))
+        lib().twin_k2a(self.h, masks.ctypes.data, n, int(max_iter), int(max_iter2), flags.ctypes.data, steps.ctypes.data,
+                       resid.ctypes.data)
+        return flags, steps, resid
+
+    def feas_from(self, ineq_rows, rhs=None):
+        """feasibility LP of one active set (inequality-row indices), optionally with a replacement rhs column (the LP seen
+        from another origin, as K2 starts from K2a's last iterate): (feasible, pivots)"""
+        act = numpy.ascontiguousarray(ineq_rows, dtype=numpy.int32)
+        piv = ctypes.c_int(0)
+        r = None if rhs is None else numpy.ascontiguousarray(rhs, dtype=numpy.float64)
+        f = lib().twin_feas_rhs(self.h, act.ctypes.data, len(act), None if r is None else r.ctypes.data, ctypes.byref(piv))
+        return bool(f), piv.value
 
     def pivots(self):
         return lib().twin_pivots(self.h)

@@ -1,0 +1,70 @@
+"""CPU checks of the feasibility-certificate algorithm (K2a) and of the K2a -> K2 hand-over, on the sequential restatement
+in oracle/twin.cpp, against the reference's golden status bytes (no GPU needed):
+  * soundness: a candidate the relaxation certifies is feasible for the reference (bit 1 of the golden status);
+  * the residuals handed over for an uncertified candidate are exact, and the feasibility LP seen from that point decides
+    exactly like the LP seen from the origin (it is the same LP, translated)."""
+import os
+import sys
+
+import numpy
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_names
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+CAP = 20000   # candidates per level looked at (seeded sample above that)
+
+
+def _levels(g, tw):
+    n_eq = int(g['n_eq'])
+    for lv in range(int(g['n_levels'])):
+        c, st = g[f'level{lv}_candidates'], g[f'level{lv}_status']
+        if len(c) == 0 or c.shape[1] - n_eq > 8:
+            continue   # the register-resident certificate kernel covers 1..8 activated rows
+        if len(c) > CAP:
+            sel = numpy.random.default_rng(lv).choice(len(c), CAP, replace=False)
+            c, st = c[sel], st[sel]
+        yield c, st
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_certificates_are_sound_and_handover_is_exact(name):
+    from twin_binding import Twin
+    g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
+    tw = Twin.from_npz(os.path.join(GOLDEN, name + '.npz'))
+    if tw.R0 > 128:
+        pytest.skip('outside the envelope of the register-resident kernel (R0 <= 128)')
+    n_eq = int(g['n_eq'])
+    checked_lp = 0
+    for c, st in _levels(g, tw):
+        flags, steps, resid = tw.k2a(tw.masks(c.tolist()))
+        rank_ok, feasible = (st & 1) != 0, (st & 2) != 0
+        assert not numpy.any((flags == 1) & rank_ok & ~feasible), 'a certified candidate is infeasible for the reference'
+        assert numpy.all(steps <= 192)
+        # hand-over: a sample of the uncertified candidates, feasible and infeasible ones
+        todo = numpy.nonzero((flags == 0) & rank_ok)[0]
+        for i in todo[:60]:
+            rows = [int(a) - n_eq for a in c[i][n_eq:]]
+            assert numpy.max(numpy.abs(resid[i][rows])) <= 1e-6 * max(1.0, numpy.max(numpy.abs(resid[i]))), \
+                'the last iterate does not satisfy the active rows'
+            cold, _ = tw.feas_from(rows)
+            warm, _ = tw.feas_from(rows, -resid[i])
+            assert cold == warm == bool(feasible[i])
+            checked_lp += 1
+    if name in ('mpc_n5', 'mpc_n7', 'rand_6_3_12_s1', 'rand_5_3_10_s2'):
+        assert checked_lp > 0   # these programs do leave candidates to the simplex
+
+
+def test_certification_rate_on_the_headline_program():
+    """levels 1-2 of the synthetic 100 x 30 x 6 program: everything that is feasible is certified (the GPU counters say
+    the same: k2a certified == tried at these levels)"""
+    from twin_binding import Twin
+    name = 'synthetic_30_6_40_s0'
+    g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
+    tw = Twin.from_npz(os.path.join(GOLDEN, name + '.npz'))
+    for c, st in _levels(g, tw):
+        flags, steps, _ = tw.k2a(tw.masks(c.tolist()))
+        ok = (st & 1) != 0
+        assert numpy.array_equal(flags[ok] == 1, ((st & 2) != 0)[ok])
+        assert 5 < steps[ok].mean() < 40
