@@ -1,6 +1,6 @@
-"""Host assembly of CriticalRegion objects from K5's buffers: the block-copy implementation must return exactly what the
-straightforward per-region statement (kept here as the reference of the test) returns - values, shapes, contiguity and
-the Python types of the index lists (field meaning: /root/reference/src/ppopt/utils/mpqp_utils.py:181-195)."""
+"""Host assembly of CriticalRegion objects from K5's buffers (engine.build_regions) against an independent per-region
+statement kept in this test: values, shapes, contiguity and the Python types of the index lists
+(field meaning: /root/reference/src/ppopt/utils/mpqp_utils.py:181-195).  Runs without a GPU."""
 import types
 
 import numpy
@@ -37,7 +37,7 @@ def _plain(eng, cr_cls, active_sets, k_act, laws, rows, flags, info):
 
 @pytest.mark.parametrize('n,t,ne,m,q,k_act', [(30, 6, 0, 100, 12, 5), (9, 2, 6, 18, 4, 3), (4, 1, 2, 12, 2, 1), (6, 3, 0, 12, 6, 6),
                                                 (5, 2, 1, 9, 4, 0)])
-def test_block_copy_assembly_equals_plain_statement(n, t, ne, m, q, k_act):
+def test_region_assembly_equals_plain_statement(n, t, ne, m, q, k_act):
     from ppopt_b200 import engine
     from ppopt_b200.critical_region import CriticalRegion
     mi = m - ne
