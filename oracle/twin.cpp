@@ -643,8 +643,9 @@ void twin_eval(void* h, const uint64_t* masks, long ncand, int final_level_lp, u
     }
 }
 
-// experiment hook: feasibility LP of one active set with an optional replacement rhs column (warm origin); returns
-// feasible flag, writes pivots; also exports the reduced feasibility rows for CPU emulations
+// feasibility LP of one active set with an optional replacement rhs column (the LP seen from another origin, as K2 starts
+// from K2a's last iterate); returns the feasible flag, writes the pivot count.  twin_rows / twin_nfree / twin_t0 export the
+// reduced feasibility rows for CPU emulations of the relaxation (tests/test_twin_k2a.py, step-count studies)
 int twin_feas_rhs(void* h, const int* act, int k, const double* rhs, int* pivots_out) {
     Twin& tw = *(Twin*)h;
     const ReducedProgram& P = tw.P;
