@@ -1,13 +1,16 @@
-"""Imports the UNMODIFIED reference (PPOPT) from /root/reference/src under the LP shim.
+"""Imports the UNMODIFIED reference (PPOPT) under the LP shim.
 
-TEST INFRASTRUCTURE.  Only usable in the build container (where /root/reference exists);
-used by oracle/gen_golden.py to produce tests/golden/* and by local (non-gpu) tests that
-skip when the reference is absent.  Nothing under ppopt_b200/ imports this.
+TEST INFRASTRUCTURE.  The reference is taken from ``baseline/_ref`` (the offline ``pip install --target`` of
+/root/reference recorded in DESIGN.md section 9; git-ignored, but it travels to the GPU box with the snapshot), else from
+/root/reference/src (build container only).  Used by oracle/gen_golden.py to produce tests/golden/*, by bench.py's
+reference arm, and by tests that skip when the reference is absent.  Nothing under ppopt_b200/ imports this.
 """
 import os
 import sys
 
-REF_SRC = '/root/reference/src'
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.path.join(_ROOT, 'baseline', '_ref'), '/root/reference/src']
+REF_SRC = next((p for p in _CANDIDATES if os.path.isdir(os.path.join(p, 'ppopt'))), _CANDIDATES[-1])
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_shim')
 
 

@@ -239,7 +239,7 @@ int feas_check(Twin& tw, const std::vector<int>& act, double* margin_out, int* c
 // rows a.theta <= f, layout [f | a(t)], returns: 0 not optimal, 1 screen passed; radius in *rad
 // zero-row rule and normalisation as in gen_cr_from_active_set (mpqp_utils.py:123-126)
 int polytope_test(Twin& tw, std::vector<double>& rows, int nrows, int t, double thr, bool strict, double* rad,
-                  std::vector<int>* nonzero_flags) {
+                  std::vector<int>* nonzero_flags, double early_extra = 0.0) {
     std::vector<int> keep;
     bool zero_violation = false;
     for (int i = 0; i < nrows; ++i) {
@@ -272,7 +272,7 @@ int polytope_test(Twin& tw, std::vector<double>& rows, int nrows, int t, double 
         for (int c = 1; c <= t; ++c) lp.at((int)ii, c) = r[c];
         lp.at((int)ii, lp.js) = 1.0;
     }
-    LpResult res = lp_maxmin(lp, thr, strict);
+    LpResult res = lp_maxmin(lp, thr + early_extra, strict);   // stops early only beyond thr + early_extra
     tw.lp_pivots += lp.pivots;
     if (rad) *rad = res.beta;
     if (res.code == PPG_LP_EARLY) return 1;
@@ -415,7 +415,9 @@ int emit_region(Twin& tw, const std::vector<int>& act, double* laws_out, double*
     }
     std::vector<int> nz(R0, 0);
     double rad = 0.0;
-    const int ok = polytope_test(tw, rows, R0, t, t == 1 ? PPG_WIDTH_1D : PPG_RADIUS, t != 1, &rad, &nz);
+    // t > 1: the LP only stops early beyond PPG_RADIUS_BAND, so that `rad` is the exact radius whenever it matters
+    const int ok = polytope_test(tw, rows, R0, t, t == 1 ? PPG_WIDTH_1D : PPG_RADIUS, t != 1, &rad, &nz,
+                                 t == 1 ? 0.0 : PPG_RADIUS_BAND);
     for (int i = 0; i < R0; ++i) flags_out[i] = nz[i] ? 1 : 0;
     for (size_t i = 0; i < rows.size(); ++i) rows_out[i] = rows[i];
     info[1] = rad;
@@ -584,6 +586,150 @@ K2aOut k2a_certify(const ReducedProgram& P, const std::vector<int>& act, int max
     return out;
 }
 
+
+// ---- K2a, prefix form: sequential statement of k2p_relax_kernel (ppopt_b200/csrc/k2p_prefix.cu) -----------------------
+// Gram matrix projected once per PREFIX (all active rows but the last two) through the numeric W = S_P^-1 Gam[P,:], the
+// candidate's own two rows deflated by a 2x2 solve, point carried as a coefficient vector over the generators, exact
+// verification of every row from the coefficients.  Same constants and stall logic as the kernel; the step length uses
+// an exact reciprocal (the kernel: MUFU.RCP64H), so step counts may differ by a few.
+K2aOut k2p_certify(const ReducedProgram& P, const std::vector<int>& act, int max_iter, int max_iter2) {
+    const int R0 = P.R0, k = (int)act.size(), dc = P.nfree + 2;
+    K2aOut out{0, 0, {}};
+    if (k < 1) return out;
+    const int p = k >= 2 ? k - 2 : 0;
+    const bool has_b = k >= 2;
+    auto G = [&](int i, int j) { return P.Gam[(size_t)i * R0 + j]; };
+    auto h = [&](int r) { return P.T0[(size_t)r * dc]; };
+    // LDL' of S_P, W, w0
+    std::vector<double> Sp((size_t)p * p), Wt((size_t)p * R0), w0(p);
+    for (int a = 0; a < p; ++a) for (int b = 0; b < p; ++b) Sp[(size_t)a * p + b] = G(act[a], act[b]);
+    for (int j = 0; j < p; ++j) {
+        const double d = Sp[(size_t)j * p + j];
+        if (!(d > 1e-12)) return out;
+        for (int i = j + 1; i < p; ++i) {
+            const double lij = Sp[(size_t)i * p + j] / d;
+            for (int c = j + 1; c <= i; ++c) Sp[(size_t)i * p + c] = std::fma(-lij, Sp[(size_t)c * p + j], Sp[(size_t)i * p + c]);
+            Sp[(size_t)i * p + j] = lij;
+        }
+    }
+    auto solveP = [&](auto get, auto set) {
+        for (int i = 1; i < p; ++i) { double x = get(i); for (int c = 0; c < i; ++c) x = std::fma(-Sp[(size_t)i * p + c], get(c), x); set(i, x); }
+        for (int i = 0; i < p; ++i) set(i, get(i) / Sp[(size_t)i * p + i]);
+        for (int i = p - 2; i >= 0; --i) { double x = get(i); for (int c = i + 1; c < p; ++c) x = std::fma(-Sp[(size_t)c * p + i], get(c), x); set(i, x); }
+    };
+    for (int j = 0; j < R0; ++j) {
+        for (int a = 0; a < p; ++a) Wt[(size_t)a * R0 + j] = G(act[a], j);
+        solveP([&](int i) { return Wt[(size_t)i * R0 + j]; }, [&](int i, double x) { Wt[(size_t)i * R0 + j] = x; });
+    }
+    for (int a = 0; a < p; ++a) w0[a] = h(act[a]);
+    solveP([&](int i) { return w0[i]; }, [&](int i, double x) { w0[i] = x; });
+    std::vector<double> Gp((size_t)R0 * R0), v0(R0);
+    for (int j = 0; j < R0; ++j)
+        for (int r = 0; r < R0; ++r) {
+            double x = G(j, r);
+            for (int a = 0; a < p; ++a) x = std::fma(-G(act[a], r), Wt[(size_t)a * R0 + j], x);
+            Gp[(size_t)j * R0 + r] = x;
+        }
+    for (int r = 0; r < R0; ++r) {
+        double x = -h(r);
+        for (int a = 0; a < p; ++a) x = std::fma(G(act[a], r), w0[a], x);
+        v0[r] = x;
+    }
+    const int b_row = act[k - 1], a_row = has_b ? act[k - 2] : b_row;
+    auto gp = [&](int j, int r) { return Gp[(size_t)j * R0 + r]; };
+    const double s11 = gp(a_row, a_row), s12 = has_b ? gp(a_row, b_row) : 0.0, s22 = has_b ? gp(b_row, b_row) : 1.0;
+    const double det = std::fma(s11, s22, -s12 * s12);
+    if (!(s11 > 1e-12 && s22 > 1e-12 && det > 1e-12 * s11 * s22)) return out;
+    const double dinv = 1.0 / det;
+    const double i11 = s22 * dinv, i12 = -s12 * dinv, i22 = has_b ? s11 * dinv : 0.0;
+    std::vector<char> park(R0, 0);
+    for (int a : act) park[a] = 1;
+    std::vector<double> v(R0), coef(R0, 0.0), s(R0);
+    {
+        const double va = v0[a_row], vb = has_b ? v0[b_row] : 0.0;
+        const double xa = std::fma(i11, va, i12 * vb), xb = std::fma(i12, va, i22 * vb);
+        for (int r = 0; r < R0; ++r) {
+            const double cb = has_b ? gp(b_row, r) : 0.0;
+            v[r] = park[r] ? -1e300 : std::fma(-xb, cb, std::fma(-xa, gp(a_row, r), v0[r]));
+        }
+    }
+    auto exact = [&]() {
+        for (int r = 0; r < R0; ++r) s[r] = v0[r];
+        double ua = v0[a_row], ub = has_b ? v0[b_row] : 0.0;
+        for (int j = 0; j < R0; ++j) {
+            if (coef[j] == 0.0) continue;
+            for (int r = 0; r < R0; ++r) s[r] = std::fma(coef[j], gp(j, r), s[r]);
+            ua = std::fma(coef[j], gp(j, a_row), ua);
+            ub = std::fma(coef[j], gp(j, b_row), ub);
+        }
+        if (!has_b) ub = 0.0;
+        const double xa = -std::fma(i11, ua, i12 * ub), xb = -std::fma(i12, ua, i22 * ub);
+        for (int r = 0; r < R0; ++r) s[r] = std::fma(xa, gp(a_row, r), std::fma(xb, has_b ? gp(b_row, r) : 0.0, s[r]));
+    };
+    const int ktol = (hi_word(PPG_FEAS_TOL * 0.999) & ~127) | 127;
+    double omega = 1.35;
+    int left = max_iter, chk = 0, wref = 0, rechecks = 0, nst = 0;
+    bool second = max_iter2 <= 0, first = true, feasible = false;
+    for (;;) {
+        int wkey = 0;
+        for (int r = 0; r < R0; ++r) wkey = std::max(wkey, (hi_word(v[r]) & ~127) | r);
+        int mode = 0;
+        if (wkey <= ktol) {
+            mode = 1;
+        } else if (std::min(chk, left) <= 0) {
+            bool stalled = left <= 0;
+            if (!stalled) { stalled = !first && wkey > wref - 0x100000; wref = wkey; chk = second ? 48 : 16; }
+            if (stalled) {
+                if (second) mode = 2;
+                else { second = true; omega = 1.8; left = max_iter2; wref = wkey; chk = 48; }
+            }
+        }
+        first = false; --chk; --left;
+        if (mode == 0) {
+            const int j = wkey & 127;
+            const double ga = gp(j, a_row), gb = gp(j, b_row);
+            const double m0 = std::fma(ga, i11, gb * i12), m1 = std::fma(ga, i12, gb * i22);
+            const double nn = std::fma(-m1, gb, std::fma(-m0, ga, gp(j, j)));
+            if (!(nn > 1e-12)) {
+                mode = 2;
+            } else {
+                const double tau = (omega * from_hi(wkey & ~127)) * (1.0 / nn);
+                const double t0 = tau * m0, t1 = tau * m1;
+                for (int r = 0; r < R0; ++r) {
+                    const double cb = has_b ? gp(b_row, r) : 0.0;
+                    v[r] = std::fma(t1, cb, std::fma(t0, gp(a_row, r), std::fma(-tau, gp(j, r), v[r])));
+                }
+                coef[j] -= tau;
+                ++nst;
+            }
+        }
+        if (mode != 0) {
+            exact();
+            double worst = 0.0;
+            for (int r = 0; r < R0; ++r) worst = std::fmax(worst, park[r] ? std::fabs(s[r]) : s[r]);
+            if (mode == 1 && worst <= PPG_FEAS_TOL) { feasible = true; break; }
+            if (mode == 1 && rechecks < 3) {
+                ++rechecks;
+                for (int r = 0; r < R0; ++r) v[r] = park[r] ? -1e300 : s[r];
+                continue;
+            }
+            break;
+        }
+    }
+    out.certified = feasible ? 1 : 0;
+    out.steps = nst;
+    if (!feasible) {
+        // the simplex may only start from this point if its residual vector is trustworthy: on an ill-conditioned prefix
+        // the projector W is large, the rounding of Gp (eps |W|) shows up as non-zero residuals on the active rows, and
+        // every other row carries the same noise - such candidates go to the simplex cold (resid[0] = NaN)
+        double eqmax = 0.0, smax = 1.0;
+        for (int r = 0; r < R0; ++r) { smax = std::fmax(smax, std::fabs(s[r])); if (park[r]) eqmax = std::fmax(eqmax, std::fabs(s[r])); }
+        out.resid = s;
+        if (!(eqmax <= 1e-9 * smax)) out.resid[0] = NAN;
+    }
+    return out;
+}
+
 }  // namespace
 
 extern "C" {
@@ -623,6 +769,7 @@ void twin_eval(void* h, const uint64_t* masks, long ncand, int final_level_lp, u
             if (P.is_qp && P.use_gram) {
                 screen = kkt_cheb_gram(tw, act, &rad);
                 if (screen < 0) { st |= PPG_ST_NUMERIC; screen = 0; }
+                if (!screen && P.t > 1 && rad >= -PPG_RADIUS_BAND && rad < PPG_RADIUS_SCREEN) st |= PPG_ST_THIN;
             } else if (P.is_qp) {
                 screen = 1;
             } else {
@@ -635,6 +782,7 @@ void twin_eval(void* h, const uint64_t* masks, long ncand, int final_level_lp, u
                 if (r < 0) st |= PPG_ST_NUMERIC;
                 if (r > 0) st |= PPG_ST_REGION;
                 rad = info[1];
+                if (r >= 0 && P.t > 1 && rad >= -PPG_RADIUS_BAND && rad <= PPG_RADIUS + PPG_RADIUS_BAND) st |= PPG_ST_THIN;
             }
         }
         (void)final_level_lp;
@@ -671,18 +819,28 @@ void twin_t0(void* h, double* out) {
 
 // K2a restatement for n candidates: flags[i] = 1 certified feasible / 0 not; steps[i]; for uncertified candidates the exact
 // residuals G z* - h of the last iterate (what the kernel hands to K2) go to resid[i * R0 ..], zeros otherwise
-void twin_k2a(void* h, const uint64_t* masks, long ncand, int max_iter, int max_iter2, int32_t* flags, int32_t* steps,
-              double* resid) {
+static void twin_k2a_any(void* h, const uint64_t* masks, long ncand, int max_iter, int max_iter2, int32_t* flags, int32_t* steps,
+                         double* resid, bool prefix) {
     Twin& tw = *(Twin*)h;
     const ReducedProgram& P = tw.P;
     std::vector<int> act;
     for (long ci = 0; ci < ncand; ++ci) {
         active_list(P, masks + ci * P.W, act);
-        K2aOut o = k2a_certify(P, act, max_iter, max_iter2);
+        K2aOut o = prefix ? k2p_certify(P, act, max_iter, max_iter2) : k2a_certify(P, act, max_iter, max_iter2);
         flags[ci] = o.certified;
         steps[ci] = o.steps;
         if (resid) for (int r = 0; r < P.R0; ++r) resid[(size_t)ci * P.R0 + r] = o.resid.empty() ? 0.0 : o.resid[r];
     }
+}
+
+void twin_k2a(void* h, const uint64_t* masks, long ncand, int max_iter, int max_iter2, int32_t* flags, int32_t* steps,
+              double* resid) {
+    twin_k2a_any(h, masks, ncand, max_iter, max_iter2, flags, steps, resid, false);
+}
+// the prefix form (k2p_prefix.cu), same outputs
+void twin_k2p(void* h, const uint64_t* masks, long ncand, int max_iter, int max_iter2, int32_t* flags, int32_t* steps,
+              double* resid) {
+    twin_k2a_any(h, masks, ncand, max_iter, max_iter2, flags, steps, resid, true);
 }
 
 int twin_emit(void* h, const uint64_t* mask, double* laws_out, double* rows_out, int32_t* flags_out, double* info) {

@@ -27,6 +27,7 @@ def lib():
         l.twin_emit.argtypes = [ctypes.c_void_p] * 6
         l.twin_emit_margins.argtypes = [ctypes.c_void_p] * 7
         l.twin_k2a.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+        l.twin_k2p.argtypes = l.twin_k2a.argtypes
         l.twin_feas_rhs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _lib = l
     return _lib
@@ -87,14 +88,15 @@ class Twin:
         rc = lib().twin_emit(self.h, mask.ctypes.data, laws.ctypes.data, rows.ctypes.data, flags.ctypes.data, info.ctypes.data)
         return rc, laws, rows, flags, info
 
-    def k2a(self, masks, max_iter=96, max_iter2=96):
-        """sequential K2a (relaxation certificates): (certified flags, steps, exact residuals of the uncertified ones)"""
+    def k2a(self, masks, max_iter=96, max_iter2=96, prefix=False):
+        """sequential K2a (relaxation certificates): (certified flags, steps, exact residuals of the uncertified ones);
+        prefix=True: the prefix-projected form of csrc/k2p_prefix.cu instead of the per-candidate form of k2a_relax.cu"""
         masks = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(-1, self.W)
         n = masks.shape[0]
         flags, steps = numpy.zeros(n, dtype=numpy.int32), numpy.zeros(n, dtype=numpy.int32)
         resid = numpy.zeros((n, self.R0))
-        lib().twin_k2a(self.h, masks.ctypes.data, n, int(max_iter), int(max_iter2), flags.ctypes.data, steps.ctypes.data,
-                       resid.ctypes.data)
+        (lib().twin_k2p if prefix else lib().twin_k2a)(self.h, masks.ctypes.data, n, int(max_iter), int(max_iter2),
+                                                       flags.ctypes.data, steps.ctypes.data, resid.ctypes.data)
         return flags, steps, resid
 
     def feas_from(self, ineq_rows, rhs=None):

@@ -608,6 +608,12 @@ static cudaError_t launch_k2a_reg_k(const DevProgram& P, const uint64_t* masks, 
 cudaError_t launch_k2a(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count, cudaStream_t st) {
     if (k_act > 32 || P.nfree > 64) return cudaSuccess;  // outside the certificate kernel's envelope: K2 decides alone
+    {
+        // production path: Gram matrix projected once per prefix in shared memory, half a warp per candidate (k2p_prefix.cu)
+        bool handled = false;
+        const cudaError_t e = launch_k2a_prefix(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st, &handled);
+        if (e != cudaSuccess || handled) return e;
+    }
     if (k_act >= 1 && k_act <= 8 && P.R0 <= 128) {
         if (k_act <= 3) return launch_k2a_reg_k<3>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);
         if (k_act == 4) return launch_k2a_reg_k<4>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st);

@@ -200,7 +200,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
             __syncwarp();
         }
         bool pass = false;
-        bool numeric = false;
+        bool numeric = false, thin = false;
         if (!pd) {
             numeric = true;
         } else {
@@ -317,6 +317,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
                     });
                     LpOut res = Core::solve(sh, T, rflag, P.R0, t1, PPG_RADIUS_SCREEN, false, lane);
                     pass = res.code == PPG_LP_EARLY || (res.code == PPG_LP_OPTIMAL && res.beta >= PPG_RADIUS_SCREEN);
+                    thin = res.code == PPG_LP_OPTIMAL && !pass && res.beta >= -PPG_RADIUS_BAND;
                     if (res.code == PPG_LP_ITERLIM) numeric = true;
                     n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
                 }
@@ -325,6 +326,7 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
         if (lane == 0) {
             uint8_t s2 = st;
             if (pass) s2 |= PPG_ST_OPT;
+            if (thin) s2 |= PPG_ST_THIN;
             if (numeric) { s2 |= PPG_ST_NUMERIC; n_num++; }
             if (s2 != st || use_pre) status[idx] = s2;
         }

@@ -33,6 +33,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
     __shared__ double s_info[4];
     __shared__ int s_ok;    // KKT solved and no zero row with negative rhs
     __shared__ int s_full;  // full-dimension test passed
+    __shared__ int s_thin;  // ... with a radius inside PPG_RADIUS_BAND of the threshold
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = P.n, t = P.t, t1 = P.t + 1, m = P.m, ne = P.ne, mi = P.mi, R0 = P.R0, W = P.W;
     const int k = ne + k_act, N = n + k, ld = N + t1;
@@ -48,7 +49,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
         const uint64_t* mk = masks + idx * W;
         __syncthreads();
         for (int j = tid; j < k; j += K5_THREADS) actf[j] = j < ne ? j : ne + mask_nth(mk, W, j - ne);
-        if (tid == 0) { s_ok = 1; s_full = 0; s_info[0] = 0.0; s_info[1] = -CUDART_INF; s_info[2] = -CUDART_INF; s_info[3] = CUDART_INF; }
+        if (tid == 0) { s_ok = 1; s_full = 0; s_thin = 0; s_info[0] = 0.0; s_info[1] = -CUDART_INF; s_info[2] = -CUDART_INF; s_info[3] = CUDART_INF; }
         __syncthreads();
         // ---- KKT matrix
         for (int e = tid; e < N * ld; e += K5_THREADS) {
@@ -212,10 +213,14 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
                         for (int c = 0; c < DC; ++c) T[rr][c] = (on && c < t1) ? rows[(size_t)row * t1 + c] : ((on && c == t1) ? 1.0 : 0.0);
                         rflag[rr] = on ? 1 : 0;
                     });
-                    LpOut res = Core::solve(sh_all[0], T, rflag, R0, t1, PPG_RADIUS, true, lane);
+                    // early exit only beyond the band: inside it the exact radius decides and the candidate is flagged
+                    LpOut res = Core::solve(sh_all[0], T, rflag, R0, t1, PPG_RADIUS + PPG_RADIUS_BAND, true, lane);
                     n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
                     const bool ok = res.code == PPG_LP_EARLY || (res.code == PPG_LP_OPTIMAL && res.beta > PPG_RADIUS);
-                    if (lane == 0) { s_info[1] = res.beta; s_full = ok ? 1 : 0; }
+                    if (lane == 0) {
+                        s_info[1] = res.beta; s_full = ok ? 1 : 0;
+                        s_thin = (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_RADIUS_BAND) ? 1 : 0;
+                    }
                 }
             }
             __syncthreads();
@@ -283,6 +288,7 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
             info_out[si * 4 + 3] = s_info[3];
             uint8_t st = status[idx];
             if (region) st |= PPG_ST_REGION;
+            if (s_thin && !singular) st |= PPG_ST_THIN;
             if (singular) st |= PPG_ST_NUMERIC;
             status[idx] = st;
         }

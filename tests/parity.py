@@ -2,6 +2,23 @@
 import numpy
 
 REL_TOL = 1e-8  # north_star: law / half-space matrices within 1e-8 relative after PPOPT's own row normalisation
+ST_THIN = 64    # csrc/tolerances.h PPG_ST_THIN: full-dimension decision inside the LP backend's tolerance band
+
+
+def check_status_bits(mine, ref, what=''):
+    """rank (1) and feasible (2) must agree on every candidate.  The region bit (8) must agree too, except on candidates
+    that the engine itself flagged PPG_ST_THIN: there the reference's answer is its LP backend's rounding (HiGHS reports a
+    radius of 2.78e-8 for polytopes whose exact radius is -7.78e-9), the engine answers with the
+    accurate radius and says so.  Returns the indices of such tolerated candidates."""
+    mine = numpy.asarray(mine)
+    ref = numpy.asarray(ref)
+    for bit, name in ((1, 'rank'), (2, 'feasible')):
+        bad = numpy.nonzero((mine & bit) != (ref & bit))[0]
+        assert bad.size == 0, f'{what}: {name} differs at {bad[:5].tolist()}'
+    bad = numpy.nonzero((mine & 8) != (ref & 8))[0]
+    untolerated = [int(i) for i in bad if not (mine[i] & ST_THIN)]
+    assert not untolerated, f'{what}: region decision differs at {untolerated[:5]} (not flagged thin)'
+    return bad
 
 
 def rel_err(a, b):
