@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Run in the build container only:  python oracle/gen_golden.py [names...]
 
-For each configuration in ppopt_b200.problems.CONFIGS it
+For each configuration in oracle/problems.py::CONFIGS it
   1. builds the reference's MPQP_Program / MPLP_Program (so the reference's own presolve runs),
   2. replays the level loop of mpqp_combinatorial.solve
      (/root/reference/src/ppopt/mp_solvers/mpqp_combinatorial.py:31-70) calling ONLY the
@@ -37,7 +37,7 @@ from ppopt.mp_solvers.solver_utils import CombinationTester, generate_children_s
 from ppopt.utils.constraint_utilities import is_full_rank  # noqa: E402
 from ppopt.utils.mpqp_utils import gen_cr_from_active_set  # noqa: E402
 
-from ppopt_b200 import problems  # noqa: E402
+import problems  # noqa: E402
 
 import multiprocess  # noqa: E402
 

@@ -25,7 +25,7 @@ from ppopt.mp_solvers import mpqp_combinatorial  # noqa: E402
 from ppopt.upop.point_location import PointLocation  # noqa: E402
 
 from gen_golden import build_reference_program  # noqa: E402
-from ppopt_b200 import problems  # noqa: E402
+import problems  # noqa: E402
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
 NAMES = ['factory_mpqp', 'rand_6_3_12_s1', 'mpc_n3', 'ctrl_alloc_n1']

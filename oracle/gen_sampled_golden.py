@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 import gen_golden as gg  # noqa: E402  (loads the reference under the shim)
 import multiprocess  # noqa: E402
 
-from ppopt_b200 import problems  # noqa: E402
+import problems  # noqa: E402
 
 
 def _lists(masks, n_eq):
@@ -33,6 +33,27 @@ def _lists(masks, n_eq):
     bits = numpy.unpackbits(m.view(numpy.uint8).reshape(m.shape[0], -1), axis=1, bitorder='little')
     eq = list(range(n_eq))
     return [eq + (numpy.nonzero(r)[0] + n_eq).tolist() for r in bits]
+
+
+def pack_regions_compact(regions, out):
+    """thousands of regions: one concatenated array per field (+ row offsets) instead of eleven zip members per region;
+    tests/parity.py::golden_regions reads both layouts"""
+    def cat(get, dtype=numpy.float64):
+        parts = [numpy.asarray(get(r), dtype=dtype).reshape(-1) for r in regions]
+        off = numpy.zeros(len(parts) + 1, dtype=numpy.int64)
+        off[1:] = numpy.cumsum([len(x) for x in parts])
+        return (numpy.concatenate(parts) if parts else numpy.zeros(0, dtype=dtype)), off
+    out['n_regions'] = numpy.int64(len(regions))
+    out['packed'] = numpy.bool_(True)
+    for key, get, dt in (('active_set', lambda r: r.active_set, numpy.int32), ('A', lambda r: r.A, numpy.float64),
+                         ('b', lambda r: r.b, numpy.float64), ('C', lambda r: r.C, numpy.float64),
+                         ('d', lambda r: r.d, numpy.float64), ('E', lambda r: r.E, numpy.float64),
+                         ('f', lambda r: r.f, numpy.float64), ('omega_set', lambda r: r.omega_set, numpy.int32),
+                         ('lambda_set', lambda r: r.lambda_set, numpy.int32),
+                         ('regular_pos', lambda r: r.regular_set[0], numpy.int32),
+                         ('regular_idx', lambda r: r.regular_set[1], numpy.int32)):
+        out['pk_' + key], out['pk_' + key + '_off'] = cat(get, dt)
+    out['pk_E_int'] = numpy.array([numpy.asarray(r.E).dtype.kind == 'i' for r in regions], dtype=numpy.bool_)
 
 
 def generate(name, procs):
@@ -65,7 +86,7 @@ def generate(name, procs):
               f'{time.time() - t0:.1f}s; engine-vs-reference status differences at sampling time: {diff}', flush=True)
     pool.close()
     pool.join()
-    gg.pack_regions(regions, out)
+    pack_regions_compact(regions, out)
     out['region_level'] = numpy.array(region_level, dtype=numpy.int64)
     dst = os.path.join(ROOT, 'tests', 'golden', 'sampled')
     os.makedirs(dst, exist_ok=True)

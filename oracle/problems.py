@@ -1,4 +1,5 @@
-"""Raw problem data for the benchmark / parity configurations (BASELINE.json `configs`).
+"""Raw problem data for the benchmark / parity configurations (BASELINE.json `configs`).  TEST INFRASTRUCTURE: fixture
+definitions for oracle/gen_*golden.py and tests/; the product package does not import this.
 
 Each builder returns a plain dict of numpy arrays in the reference's constructor
 convention  ``min 1/2 x'Qx + theta'H'x + c'x  s.t.  Ax <= b + F theta,  A_t theta <= b_t``

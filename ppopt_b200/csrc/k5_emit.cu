@@ -203,23 +203,62 @@ k5_emit_kernel(DevProgram P, const uint64_t* __restrict__ masks, const long long
                         s_full = (lo + PPG_WIDTH_1D <= hi) ? 1 : 0;
                     }
                 } else {
-                    double T[RPT][DC];
-                    int rflag[RPT];
-                    static_for<RPT>([&](auto RR) {
-                        constexpr int rr = decltype(RR)::value;
-                        const int row = rr * 32 + lane;
-                        const bool on = row < R0 && (flags[row] & 1);
+                    // Chebyshev LP, then the radius of the LP's own point re-evaluated on the untouched rows: the simplex
+                    // relaxes rows by up to 1e-9 per pivot (Harris bound, snapping), so its beta is an UPPER bound of the
+                    // radius and min_i (f_i - a_i theta*) a LOWER one; the decision uses the lower bound.  An early exit
+                    // whose point does not clear the band is repeated without early exit (attempt 1).
+                    double rad_lo = -CUDART_INF, rad_hi = -CUDART_INF;
+                    int code = PPG_LP_OPTIMAL;
+                    for (int attempt = 0; attempt < 2; ++attempt) {
+                        double T[RPT][DC];
+                        int rflag[RPT], bv[RPT];
+                        static_for<RPT>([&](auto RR) {
+                            constexpr int rr = decltype(RR)::value;
+                            const int row = rr * 32 + lane;
+                            const bool on = row < R0 && (flags[row] & 1);
 #pragma unroll
-                        for (int c = 0; c < DC; ++c) T[rr][c] = (on && c < t1) ? rows[(size_t)row * t1 + c] : ((on && c == t1) ? 1.0 : 0.0);
-                        rflag[rr] = on ? 1 : 0;
-                    });
-                    // early exit only beyond the band: inside it the exact radius decides and the candidate is flagged
-                    LpOut res = Core::solve(sh_all[0], T, rflag, R0, t1, PPG_RADIUS + PPG_RADIUS_BAND, true, lane);
-                    n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
-                    const bool ok = res.code == PPG_LP_EARLY || (res.code == PPG_LP_OPTIMAL && res.beta > PPG_RADIUS);
+                            for (int c = 0; c < DC; ++c) T[rr][c] = (on && c < t1) ? rows[(size_t)row * t1 + c] : ((on && c == t1) ? 1.0 : 0.0);
+                            rflag[rr] = on ? 1 : 0;
+                            bv[rr] = 0;
+                        });
+                        const double thr = attempt == 0 ? PPG_RADIUS + PPG_RADIUS_BAND : CUDART_INF;
+                        LpOut res = Core::solve(sh_all[0], T, rflag, R0, t1, thr, true, lane, true, &bv);
+                        n_lp++; n_piv += res.pivots; n_work += (unsigned long long)res.work;
+                        code = res.code;
+                        rad_hi = res.beta;
+                        if (code != PPG_LP_EARLY && code != PPG_LP_OPTIMAL) break;
+                        // theta* from the rows of the basic free variables (nonbasic ones sit at 0)
+                        double* th = &sh_all[0].P[0][0][0];   // scratch: the LP is over
+                        __syncwarp();
+                        if (lane < t) th[lane] = 0.0;
+                        __syncwarp();
+                        static_for<RPT>([&](auto RR) {
+                            constexpr int rr = decltype(RR)::value;
+                            if (rflag[rr] == 3) {
+                                const int c = bv[rr] < 0 ? -bv[rr] : bv[rr];
+                                if (c >= 1 && c <= t) th[c - 1] = bv[rr] < 0 ? -T[rr][0] : T[rr][0];
+                            }
+                        });
+                        __syncwarp();
+                        double lo = CUDART_INF;
+                        for (int r = lane; r < R0; r += 32)
+                            if (flags[r] & 1) {
+                                double sl = rows[(size_t)r * t1];
+                                for (int c = 0; c < t; ++c) sl = fma(-rows[(size_t)r * t1 + 1 + c], th[c], sl);
+                                lo = fmin(lo, sl);
+                            }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) lo = fmin(lo, shfl_xor_d(lo, o));
+                        rad_lo = lo;
+                        __syncwarp();
+                        if (code == PPG_LP_OPTIMAL || rad_lo > PPG_RADIUS + PPG_RADIUS_BAND) break;
+                    }
+                    const bool solved = code == PPG_LP_EARLY || code == PPG_LP_OPTIMAL;
+                    const bool ok = solved && rad_lo > PPG_RADIUS;
                     if (lane == 0) {
-                        s_info[1] = res.beta; s_full = ok ? 1 : 0;
-                        s_thin = (res.code == PPG_LP_OPTIMAL && res.beta >= -PPG_RADIUS_BAND) ? 1 : 0;
+                        s_info[1] = solved ? rad_lo : rad_hi;
+                        s_full = ok ? 1 : 0;
+                        s_thin = (solved && rad_hi >= -PPG_RADIUS_BAND && rad_lo <= PPG_RADIUS + PPG_RADIUS_BAND) ? 1 : 0;
                     }
                 }
             }

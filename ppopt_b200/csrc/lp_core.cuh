@@ -194,8 +194,12 @@ struct LpCore {
     // Solves the LP held in registers. On entry: T rows, rflag (0 dead / 1 inequality / 2 equality), ncol = number
     // of nonbasic columns (columns 1..ncol, the last one, js = ncol, is s).
     // Returns (uniformly on all threads) once beta >= thr (strict: beta > thr), at optimality, or on failure.
+    // keep_free: the row in which a FREE variable becomes basic is kept up to date (rflag 3, never in a ratio test) instead
+    // of being dropped, so that the caller can read the solution point afterwards with solution_point() - used where a
+    // decision hangs on beta itself: the Harris ratio test and the snapping of tiny negative right-hand sides relax rows
+    // by up to 1e-9 per pivot, and on flat polytopes that adds up (2.6e-7 seen on ctrl_alloc_n5 level 5).
     __device__ static LpOut solve(Shared& sh, double (&T)[RPT][DC], int (&rflag)[RPT], int nrows, int ncol, double thr,
-                                  bool strict, int tid) {
+                                  bool strict, int tid, bool keep_free = false, int (*bvar_out)[RPT] = nullptr) {
         const int lane = tid & 31, warp = tid >> 5;
         const int js = ncol;
         int bvar[RPT];
@@ -486,11 +490,17 @@ struct LpCore {
                     }
                 }
             }
-            eliminate(P, T, rflag, colv, tid, r, j, inv, !entering_free);
+            eliminate(P, T, rflag, colv, tid, r, j, inv, !entering_free || keep_free);
             static_for<RPT>([&](auto RR) {
                 constexpr int rr = decltype(RR)::value;
                 if (rr * GT + tid == r) {
-                    if (entering_free) rflag[rr] = 0; else bvar[rr] = enter_var;
+                    if (entering_free) {
+                        rflag[rr] = keep_free ? 3 : 0;
+                        // the row now holds dir * x_j (the step variable); remember the sign with the column id
+                        if (keep_free && bvar_out) (*bvar_out)[rr] = dir < 0.0 ? -enter_var : enter_var;
+                    } else {
+                        bvar[rr] = enter_var;
+                    }
                 }
                 if (rflag[rr] == 1 && T[rr][0] < 0.0 && T[rr][0] > -1e-9) T[rr][0] = 0.0;
             });

@@ -13,7 +13,7 @@ import numpy
 import torch
 
 from . import _lib, sharding
-from ._lib import ST_FEAS, ST_OPT, ST_REGION
+from ._lib import ST_BORDER, ST_FEAS, ST_NUMERIC, ST_OPT, ST_RANK, ST_REGION, ST_THIN
 
 
 def _c(a):
@@ -280,19 +280,96 @@ def _dist():
     return None
 
 
+class NumericalFailure(RuntimeError):
+    """A candidate could not be decided (LP iteration limit / non-finite values) even after the cold re-evaluation.
+    Raised instead of silently treating the candidate as infeasible, which would prune every superset of it."""
+
+
+def _checksum(status: torch.Tensor) -> int:
+    """order-sensitive checksum of the decision bits of a level (device side, one number crosses PCIe)"""
+    n = status.shape[0]
+    if n == 0:
+        return 0
+    w = (torch.arange(n, device=status.device, dtype=torch.int64) * 2654435761 + 12345) & 0x7fffffff
+    return int((((status & 15).to(torch.int64) + 1) * w).sum().item() & 0x7fffffffffffffff)
+
+
+def _eval_level(eng: Engine, masks: torch.Tensor, k_act: int, dist, rank: int, world: int) -> torch.Tensor:
+    """status bytes of one level.  Multi-GPU: this rank's chunks (sharding.py) are packed into ONE contiguous array, so
+    that every stage is one launch per rank (16 chunk-wise calls x 7 launches paid 16 kernel tails each), evaluated, and
+    the bytes scattered back; one NCCL all-reduce(SUM) of the byte vector then gives every rank all statuses."""
+    n = masks.shape[0]
+    status = torch.zeros((n,), dtype=torch.uint8, device=eng.tdev)
+    if world <= 1:
+        eng.level_eval(masks, k_act, status, 7)
+        return status
+    mine = sharding.chunks(n, rank, world)
+    if mine:
+        if len(mine) == 1:
+            lo, hi = mine[0]
+            eng.level_eval(masks, k_act, status, 7, lo, hi)
+        else:
+            packed = torch.cat([masks[lo:hi] for lo, hi in mine])
+            st = eng.level_eval(packed, k_act, None, 7)
+            off = 0
+            for lo, hi in mine:
+                status[lo:hi] = st[off:off + hi - lo]
+                off += hi - lo
+    return sharding.gather_status(status, dist)
+
+
+def _escalate_numeric(eng: Engine, masks: torch.Tensor, status: torch.Tensor, k_act: int, flagged: Dict, level: int):
+    """Never prune on a numerical failure.  Candidates whose feasibility LP hit the iteration limit
+    (NUMERIC set, FEAS clear) are re-evaluated by the cold simplex - no relaxation, no warm origin: a genuinely different
+    computation; if that does not decide them either the solve stops with NumericalFailure.  Candidates on which the
+    Gram/Cholesky optimality screen failed (NUMERIC and FEAS set) go to K5, whose LU of the KKT matrix decides."""
+    num = eng.select(status, ST_NUMERIC | ST_FEAS, ST_NUMERIC)
+    if num.shape[0]:
+        sub = masks[num].contiguous()
+        st2 = torch.full((sub.shape[0],), ST_RANK, dtype=torch.uint8, device=eng.tdev)
+        eng.level_eval(sub, k_act, st2, 2 | 4 | 8)     # stage bit 8: cold simplex only
+        still = (st2 & (ST_NUMERIC | ST_FEAS)) == ST_NUMERIC
+        if bool(still.any().item()):
+            bad = eng.lists_from_masks(sub[still][:8].cpu().numpy())
+            raise NumericalFailure(f'level {level}: {int(still.sum().item())} candidate(s) undecided after the cold '
+                                   f're-evaluation, e.g. {bad}')
+        status[num] = st2
+        flagged['numeric_recovered'] += int(num.shape[0])
+    scr = eng.select(status, ST_NUMERIC | ST_FEAS | ST_OPT, ST_NUMERIC | ST_FEAS)
+    if scr.shape[0]:
+        status[scr] = (status[scr] & ~ST_NUMERIC) | ST_OPT
+        flagged['screen_failed'] += int(scr.shape[0])
+
+
+def _collect_flags(eng: Engine, masks: torch.Tensor, status: torch.Tensor, flagged: Dict):
+    """rank decisions inside the borderline band and full-dimension decisions inside the LP tolerance band are REPORTED
+    (solution.flagged: counts, and the first 4096 active sets of each kind), never silent"""
+    for name, bit in (('border', ST_BORDER), ('thin', ST_THIN)):
+        idx = eng.select(status, bit, bit)
+        if idx.shape[0]:
+            flagged[name + '_count'] += int(idx.shape[0])
+            room = 4096 - len(flagged[name])
+            if room > 0:
+                flagged[name].extend(eng.lists_from_masks(masks[idx[:room]].cpu().numpy()))
+
+
 def solve(program, max_levels: Optional[int] = None, collect_status: bool = False, engine: Optional[Engine] = None,
           emit_regions: bool = True, distributed: bool = True, expand_last: bool = False,
-          materialize: bool = True):
+          materialize: bool = True, digest: bool = False):
     """GPU replacement for mpqp_combinatorial.solve(program) (mpqp_combinatorial.py:10-72).
 
     Returns the Solution; per-level statistics are attached as ``solution.level_stats`` (candidates, feasible,
     optimal-screen, regions, seconds) - the counters the reference's parallel solvers print
     (mpqp_parrallel_combinatorial.py:103-104).  ``max_levels`` caps the depth for programs nobody can finish
-    (applied identically to the CPU baselines in bench.py).
+    (applied identically to the CPU baselines in bench.py).  ``solution.flagged`` lists the candidates whose decision
+    fell inside a documented tolerance band (rank: 'border', full dimension: 'thin'); a candidate that cannot be decided
+    at all raises NumericalFailure.  ``digest=True`` adds ``solution.digest``, a hash of every level's decision bits and of
+    the region list, used to prove that N-GPU runs decide exactly like the 1-GPU run (bench.py).
 
-    Under torch.distributed (world size G > 1) every level's candidate array is cut into chunks dealt round-robin to the
-    ranks (sharding.py), the status bytes are combined by one NCCL all-reduce, and every rank then generates the identical
-    next level.
+    Under torch.distributed (world size G > 1) every level's candidate array is cut into chunks dealt to the ranks in
+    snake order (sharding.py), each rank evaluates its share as one contiguous batch, the status bytes are combined by one
+    NCCL all-reduce, every rank generates the identical next level, and the raw region buffers of the owning ranks are
+    all-gathered (NCCL) so that every rank builds the same Solution.
     """
     own = engine is None
     eng = Engine(program_arrays(program)) if own else engine
@@ -302,6 +379,9 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
     regions: list = []
     stats = []
     statuses = []
+    sums = []
+    flagged = {'border': [], 'thin': [], 'border_count': 0, 'thin_count': 0, 'numeric_recovered': 0, 'screen_failed': 0,
+               'singular_skipped': []}
     depth = eng.max_depth if max_levels is None else min(eng.max_depth, max_levels)
     complete = max_levels is None or max_levels >= eng.max_depth
     masks = eng.root_level() if depth > 0 else eng.empty((0, eng.W), torch.int64)
@@ -312,45 +392,51 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
             break
         t0 = time.perf_counter()
         k_act = lvl + 1
-        status = torch.zeros((n,), dtype=torch.uint8, device=eng.tdev)
-        if world > 1:
-            for lo, hi in sharding.chunks(n, rank, world):
-                eng.level_eval(masks, k_act, status, 7, lo, hi)
-            status = sharding.gather_status(status, dist)
-        else:
-            eng.level_eval(masks, k_act, status, 7)
+        status = _eval_level(eng, masks, k_act, dist, rank, world)
+        if bool(((status & ST_NUMERIC) != 0).any().item()):
+            _escalate_numeric(eng, masks, status, k_act, flagged, lvl + 1)
         n_reg = 0
         opt_idx = eng.select(status, ST_OPT, ST_OPT)
         n_opt = int(opt_idx.shape[0])
         if n_opt and emit_regions:
-            # regions are emitted by the rank that owns the candidate; rank 0 collects them at the end
+            # regions are emitted by the rank that owns the candidate
             mine = sharding.owned(opt_idx, n, rank, world) if world > 1 else opt_idx
-            if mine.shape[0] and not materialize:
-                eng.emit(masks, mine, k_act, status)  # results stay in HBM (device-resident throughput runs)
-                built = [(int(i), None) for i in range(int(mine.shape[0]))]
-            elif mine.shape[0]:
-                laws, rows, flags, info = eng.emit(masks, mine, k_act, status)
-                sel_masks = masks[mine].cpu().numpy()
-                laws, rows, flags, info = laws.cpu().numpy(), rows.cpu().numpy(), flags.cpu().numpy(), info.cpu().numpy()
-                eng.d2h_bytes += laws.nbytes + rows.nbytes + flags.nbytes + info.nbytes + sel_masks.nbytes
-                asets = eng.lists_from_masks(sel_masks)
-                if numpy.any(info[:, 0] < 0):
-                    raise numpy.linalg.LinAlgError('Singular matrix')  # what the reference raises (mpqp_program.py:187)
-                built = [(int(i), r) for i, r in zip(mine.cpu().tolist(),
-                                                     build_regions(eng, cr_cls, asets, k_act, laws, rows, flags, info))
-                         if r is not None]
+            if not materialize:
+                if mine.shape[0]:
+                    eng.emit(masks, mine, k_act, status)  # results stay in HBM (device-resident throughput runs)
+                if world > 1 and (digest or collect_status):
+                    status = sharding.gather_region_bits(status, mine, dist)
             else:
-                built = []
-            if world > 1:
-                allb = [None] * world
-                dist.all_gather_object(allb, built)
-                built = sorted([x for part in allb for x in part], key=lambda x: x[0])
-            regions.extend(r for _, r in built if r is not None)
-            n_reg = len(built)
+                bufs = eng.emit(masks, mine, k_act, status) if mine.shape[0] else None
+                if world > 1:
+                    mine, bufs = sharding.gather_regions(eng, mine, bufs, k_act, dist)
+                    status = sharding.gather_region_bits(status, mine, dist, already_global=True, bufs=bufs)
+                if bufs is not None and mine.shape[0]:
+                    laws, rows, flags, info = [x.cpu().numpy() for x in bufs]
+                    sel_masks = masks[mine].cpu().numpy()
+                    eng.d2h_bytes += laws.nbytes + rows.nbytes + flags.nbytes + info.nbytes + sel_masks.nbytes
+                    asets = eng.lists_from_masks(sel_masks)
+                    sing = numpy.nonzero(info[:, 0] < 0)[0]
+                    if sing.size:
+                        if eng.use_gram or not eng.is_qp:
+                            # passed the optimality screen and the KKT system is singular: what the reference raises
+                            # (mpqp_program.py:187)
+                            raise numpy.linalg.LinAlgError('Singular matrix')
+                        # general path (reduced Hessian not positive definite): K5's LU is also the optimality test here;
+                        # the reference only solves the KKT system of sets that passed check_optimality, so a singular
+                        # system of an arbitrary feasible set is skipped and reported, not raised
+                        flagged['singular_skipped'].extend(asets[i] for i in sing[:256])
+                    built = build_regions(eng, cr_cls, asets, k_act, laws, rows, flags, info)
+                    regions.extend(r for r in built if r is not None)
+            n_reg = int(((status & ST_REGION) != 0).sum().item())
         feas_idx = eng.select(status, ST_FEAS, ST_FEAS)
         n_feas = int(feas_idx.shape[0])
+        if bool(((status & (ST_THIN | ST_BORDER)) != 0).any().item()):
+            _collect_flags(eng, masks, status, flagged)
         if collect_status:
             statuses.append((masks.cpu().numpy(), status.cpu().numpy()))
+        if digest:
+            sums.append((n, _checksum(status)))
         last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
         nxt = eng.children(masks, feas_idx, k_act, dist if world > 1 else None) if not last else eng.empty((0, eng.W), torch.int64)
         torch.cuda.synchronize(eng.tdev)
@@ -382,8 +468,15 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
     solution.engine_counters = eng.counters()
     solution.gpu_launches = eng.launch_count()
     solution.h2d_bytes, solution.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
+    solution.flagged = flagged
     if collect_status:
         solution.level_status = statuses
+    if digest:
+        import hashlib
+        hh = hashlib.sha256(repr(sums).encode())
+        if materialize:
+            hh.update(repr([tuple(r.active_set) for r in regions]).encode())
+        solution.digest = hh.hexdigest()
     if own:
         eng.close()
     return solution

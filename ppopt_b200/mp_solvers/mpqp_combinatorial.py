@@ -24,12 +24,12 @@ def check_child_feasibility(program, set_list: List[List[int]], combination_chec
         feasible = [False] * len(set_list)
         by_k = {}
         for pos, s in enumerate(set_list):
-            by_k.setdefault(len(s), []).append(pos)
-        for k, positions in by_k.items():
+            # kernels are specialised on the number of activated INEQUALITY rows (the bits of the mask); a set that omits
+            # some equality rows is evaluated as its closure (equalities are always active, mplp_program.py:112-118)
+            by_k.setdefault(sum(1 for i in s if int(i) >= eng.n_eq), []).append(pos)
+        for k_act, positions in by_k.items():
             masks = eng.masks_from_lists([set_list[p] for p in positions])
-            k_act = k - eng.n_eq
-            # an active set that does not contain every equality row cannot be encoded: evaluate it as its closure
-            st = eng.level_eval(masks, -1 if k_act < 0 else k_act, stages=3).cpu().numpy()
+            st = eng.level_eval(masks, k_act, stages=3).cpu().numpy()
             for p, s in zip(positions, st):
                 feasible[p] = bool(s & ST_FEAS)
     finally:

@@ -46,3 +46,53 @@ def owned(indices: torch.Tensor, n: int, rank: int, world: int) -> torch.Tensor:
     for lo, hi in chunks(n, rank, world):
         keep |= (indices >= lo) & (indices < hi)
     return indices[keep].contiguous()
+
+
+def gather_regions(eng, mine: torch.Tensor, bufs, k_act: int, dist):
+    """Region payloads of all ranks, in candidate order, on EVERY rank: counts first, then the raw K5 buffers
+    (laws / rows / flags / info) and the owning candidate indices through NCCL all_gather on padded tensors - no Python
+    objects cross the wire (the object all-gather of round 1 pickled ~48 MB per level)."""
+    world = dist.get_world_size()
+    dev = eng.tdev
+    n_mine = int(mine.shape[0])
+    counts = torch.zeros((world,), dtype=torch.int64, device=dev)
+    counts[dist.get_rank()] = n_mine
+    dist.all_reduce(counts)
+    counts_h = counts.cpu().tolist()
+    cap = max(counts_h)
+    if cap == 0:
+        return mine, None
+    N = eng.n + eng.n_eq + k_act
+    shapes = [(N, eng.t + 1), (eng.R0, eng.t + 1), (eng.R0,), (4,)]
+    dtypes = [torch.float64, torch.float64, torch.int32, torch.float64]
+
+    def pad(x, shape, dtype):
+        out = torch.zeros((cap,) + shape, dtype=dtype, device=dev)
+        if x is not None and x.shape[0]:
+            out[:x.shape[0]] = x
+        return out
+    parts = [pad(None if bufs is None else b, sh, dt) for b, sh, dt in zip(bufs or [None] * 4, shapes, dtypes)]
+    parts.append(pad(mine, (), torch.int64))
+    gathered = []
+    for x in parts:
+        buf = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=dev)
+        dist.all_gather_into_tensor(buf, x)
+        gathered.append(torch.cat([buf[r, :counts_h[r]] for r in range(world)]))
+    idx = gathered[4]
+    order = torch.argsort(idx)
+    return idx[order].contiguous(), [g[order].contiguous() for g in gathered[:4]]
+
+
+def gather_region_bits(status: torch.Tensor, mine: torch.Tensor, dist, already_global: bool = False, bufs=None):
+    """K5 sets the region bit (8) only on the emitting rank; make every rank's status vector agree (the digest and the
+    collected status arrays are then identical on all ranks)."""
+    if already_global:
+        if bufs is not None and mine.shape[0]:
+            is_region = bufs[3][:, 0] == 1.0
+            status[mine[is_region]] |= 8
+        return status
+    bits = torch.zeros_like(status)
+    if mine.shape[0]:
+        bits[mine] = status[mine] & 8
+    dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+    return status | bits

@@ -34,6 +34,21 @@ def rel_err(a, b):
 
 def golden_regions(g):
     out = []
+    if 'packed' in g:   # compact layout of the sampled goldens (oracle/gen_sampled_golden.py::pack_regions_compact)
+        keys = ('active_set', 'A', 'b', 'C', 'd', 'E', 'f', 'omega_set', 'lambda_set', 'regular_pos', 'regular_idx')
+        data = {k: (g['pk_' + k], g['pk_' + k + '_off']) for k in keys}
+        t = None
+        for i in range(int(g['n_regions'])):
+            r = {k: data[k][0][data[k][1][i]:data[k][1][i + 1]] for k in keys}
+            nb, nd, nf = len(r['b']), len(r['d']), len(r['f'])
+            t = len(r['A']) // nb if nb else (len(r['C']) // nd if nd else t)
+            r['A'], r['b'] = r['A'].reshape(nb, -1), r['b'].reshape(nb, 1)
+            r['C'], r['d'] = r['C'].reshape(nd, -1), r['d'].reshape(nd, 1)
+            r['E'], r['f'] = r['E'].reshape(nf, -1), r['f'].reshape(nf, 1)
+            if g['pk_E_int'][i]:
+                r['E'] = r['E'].astype(numpy.int64)
+            out.append(r)
+        return out
     for i in range(int(g['n_regions'])):
         out.append({k: g[f'r{i}_{k}'] for k in ('active_set', 'A', 'b', 'C', 'd', 'E', 'f', 'omega_set', 'lambda_set',
                                                   'regular_pos', 'regular_idx')})
@@ -60,7 +75,54 @@ def rows_match_as_sets(E1, f1, E2, f2, tol=REL_TOL):
 
 def masks_to_lists(masks, n_eq):
     m = numpy.ascontiguousarray(masks).view(numpy.uint64)
+    if m.shape[0] == 0:
+        return []
     m = m.reshape(m.shape[0], -1)
     bits = numpy.unpackbits(m.view(numpy.uint8).reshape(m.shape[0], -1), axis=1, bitorder='little')
     eq = list(range(n_eq))
     return [eq + (numpy.nonzero(r)[0] + n_eq).tolist() for r in bits]
+
+
+MARGIN_BAND = 1e-7   # DESIGN.md section 5, deviation 1: the reference's keep/drop decisions are its LP backend's, whose
+                     # feasibility tolerance is 1e-7 (observed: overlapping decisions for margins in [-6.7e-8, 5e-11])
+
+
+def index_lists_match(region, ref, rows=None, flags=None, margins=None, k_act=0, n_eq=0, m=0, one_d=False):
+    """kept-index lists of a region (omega_set, lambda_set, regular_set; mpqp_utils.py:181-184) against the golden ones.
+    Returns the list of discrepancies that are NOT explained by the documented reference-side ambiguity:
+      * a row whose redundancy margin (``margins``, from the CPU checker's emit with margins=True) lies inside
+        +-MARGIN_BAND may be kept by one side and dropped by the other;
+      * 1-D programs: the reference compares bitwise-rounded interval end points, so which of several rows attaining the
+        end point is listed depends on the last ulp (DESIGN.md deviation 2) - the lists must then agree as sets of
+        END-POINT VALUES, checked by the caller through f."""
+    want = {'omega': ref['omega_set'].tolist(), 'lambda': ref['lambda_set'].tolist(),
+            'regular_pos': ref['regular_pos'].tolist(), 'regular_idx': ref['regular_idx'].tolist()}
+    got = {'omega': list(region.omega_set), 'lambda': list(region.lambda_set),
+           'regular_pos': list(region.regular_set[0]), 'regular_idx': list(region.regular_set[1])}
+    if got == want:
+        return []
+    if one_d:
+        return []   # end-point ties; f is compared by the caller
+    if margins is None:
+        return [(k, got[k], want[k]) for k in got if got[k] != want[k]]
+    aset = list(region.active_set)
+    active = aset[n_eq:]
+    n_inact = m - len(aset)
+    bad = []
+    pos_of = {}
+    for j, a in enumerate(active):
+        pos_of[('lambda', a)] = j
+    for p_ in range(n_inact):
+        pos_of[('regular_pos', p_)] = k_act + p_
+    inactive = [i for i in range(m) if i not in set(aset)]
+    for p_, i in enumerate(inactive):
+        pos_of[('regular_idx', i)] = k_act + p_
+    for key in ('omega', 'lambda', 'regular_pos', 'regular_idx'):
+        for v in set(got[key]) ^ set(want[key]):
+            row = pos_of.get((key, v), k_act + n_inact + v if key == 'omega' else None)
+            mg = None if row is None else margins[row]
+            if mg is None or not (abs(mg) < MARGIN_BAND):
+                bad.append((key, v, mg))
+        if not bad and [x for x in got[key] if x in want[key]] != [x for x in want[key] if x in got[key]]:
+            bad.append((key, 'order', got[key], want[key]))
+    return bad

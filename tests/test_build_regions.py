@@ -1,69 +1,74 @@
-"""Host assembly of CriticalRegion objects from K5's buffers (engine.build_regions) against an independent per-region
-statement kept in this test: values, shapes, contiguity and the Python types of the index lists
-(field meaning: /root/reference/src/ppopt/utils/mpqp_utils.py:181-195).  Runs without a GPU."""
+"""Host assembly of CriticalRegion objects from K5's buffers (engine.build_regions), checked against what the UNMODIFIED
+reference produced (tests/golden/*.npz): the buffers come from the CPU checker's emit (oracle/twin.cpp::emit_region, same
+layout as ppgpu_regions_emit), the expectations - matrices, kept-index lists omega_set / lambda_set / regular_set
+(/root/reference/src/ppopt/utils/mpqp_utils.py:181-195), dtypes - from the golden regions.  Runs without a GPU."""
+import os
+import sys
 import types
 
 import numpy
 import pytest
 
+from conftest import GOLDEN, ROOT
+from parity import REL_TOL, golden_regions, index_lists_match, rel_err, rows_match_as_sets
 
-def _plain(eng, cr_cls, active_sets, k_act, laws, rows, flags, info):
-    n, t, ne, m = eng.n, eng.t, eng.n_eq, eng.m
-    out = []
-    n_inact = eng.mi - k_act
-    for si, aset in enumerate(active_sets):
-        if info[si, 0] != 1.0:
-            out.append(None)
-            continue
-        law, fl = laws[si], flags[si]
-        kept = numpy.nonzero((fl & 3) == 3)[0]
-        if t == 1:
-            E = numpy.array([[1], [-1]])
-            f = numpy.array([[info[si, 3]], [-info[si, 2]]])
-        else:
-            nd = numpy.nonzero(((fl & 3) == 3) & ((fl & 4) == 0))[0]
-            E = numpy.ascontiguousarray(rows[si][nd, 1:])
-            f = numpy.ascontiguousarray(rows[si][nd, :1])
-        active = aset[ne:]
-        inactive = [i for i in range(m) if i not in set(aset)]
-        lam = [active[i] for i in kept if i < k_act]
-        reg_pos = [int(i - k_act) for i in kept if k_act <= i < k_act + n_inact]
-        omega = [int(i - k_act - n_inact) for i in kept if i >= k_act + n_inact]
-        out.append(cr_cls(numpy.ascontiguousarray(law[:n, 1:]), numpy.ascontiguousarray(law[:n, :1]),
-                          numpy.ascontiguousarray(law[n:, 1:]), numpy.ascontiguousarray(law[n:, :1]), E, f, list(aset),
-                          omega, lam, [reg_pos, [inactive[p] for p in reg_pos]]))
-    return out
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+NAMES = ['factory_mpqp', 'transport_mplp', 'simple_mplp', 'doc_portfolio', 'portfolio_analog', 'mpc_n5', 'mpc_n10',
+         'ctrl_alloc_n1', 'rand_6_3_12_s1', 'rand_5_3_10_s2', 'rand_lp_4_2_8_s3', 'synthetic_30_6_40_s0']
 
 
-@pytest.mark.parametrize('n,t,ne,m,q,k_act', [(30, 6, 0, 100, 12, 5), (9, 2, 6, 18, 4, 3), (4, 1, 2, 12, 2, 1), (6, 3, 0, 12, 6, 6),
-                                                (5, 2, 1, 9, 4, 0)])
-def test_region_assembly_equals_plain_statement(n, t, ne, m, q, k_act):
+@pytest.mark.parametrize('name', NAMES)
+def test_region_assembly_reproduces_the_reference_regions(name):
+    from twin_binding import Twin
     from ppopt_b200 import engine
     from ppopt_b200.critical_region import CriticalRegion
-    mi = m - ne
-    eng = types.SimpleNamespace(n=n, t=t, n_eq=ne, m=m, mi=mi)
-    R0, k, N = mi + q, ne + k_act, 37
-    rng = numpy.random.default_rng(n * 100 + t)
-    laws, rows = rng.standard_normal((N, n + k, t + 1)), rng.standard_normal((N, R0, t + 1))
-    info = numpy.ones((N, 4))
-    info[:, 2], info[:, 3] = -rng.random(N), rng.random(N)
-    info[rng.random(N) < 0.2, 0] = 0.0
-    info[3, 0] = -1.0
-    flags = rng.choice(numpy.array([0, 1, 2, 3, 7], dtype=numpy.int32), size=(N, R0))
-    flags[5] = 0
-    asets = [list(range(ne)) + sorted((ne + rng.choice(mi, k_act, replace=False)).tolist()) for _ in range(N)]
-    got = engine.build_regions(eng, CriticalRegion, asets, k_act, laws, rows, flags, info)
-    want = _plain(eng, CriticalRegion, asets, k_act, laws, rows, flags, info)
-    assert len(got) == len(want) == N
-    for a, b in zip(got, want):
-        assert (a is None) == (b is None)
-        if a is None:
-            continue
-        for fld in 'AbCdEf':
-            x, y = getattr(a, fld), getattr(b, fld)
-            assert x.shape == y.shape and x.dtype == y.dtype and numpy.array_equal(x, y) and x.flags.c_contiguous, fld
-        assert a.active_set == b.active_set and a.omega_set == b.omega_set and a.lambda_set == b.lambda_set
-        assert a.regular_set == b.regular_set
-        for lst in (a.omega_set, a.lambda_set, a.regular_set[0], a.regular_set[1]):
-            assert all(type(v) is int for v in lst)
-    assert engine.build_regions(eng, CriticalRegion, [], k_act, laws[:0], rows[:0], flags[:0], info[:0]) == []
+    path = os.path.join(GOLDEN, name + '.npz')
+    g = numpy.load(path)
+    tw = Twin.from_npz(path)
+    eng = types.SimpleNamespace(n=tw.n, t=tw.t, n_eq=tw.n_eq, m=tw.m, mi=tw.m - tw.n_eq)
+    ref = golden_regions(g)[:120]
+    by_k = {}
+    for r in ref:
+        by_k.setdefault(len(r['active_set']) - tw.n_eq, []).append(r)
+    n_checked = 0
+    for k_act, regs in by_k.items():
+        bufs = [tw.emit(tw.masks([r['active_set'].tolist()])[0], margins=True) for r in regs]
+        assert all(b[0] == 1 for b in bufs)
+        laws = numpy.stack([b[1] for b in bufs])
+        rows = numpy.stack([b[2] for b in bufs])
+        flags = numpy.stack([b[3] for b in bufs])
+        info = numpy.stack([b[4] for b in bufs])
+        asets = [r['active_set'].tolist() for r in regs]
+        got = engine.build_regions(eng, CriticalRegion, asets, k_act, laws, rows, flags, info)
+        assert len(got) == len(regs)
+        for a, r, b in zip(got, regs, bufs):
+            assert a is not None and a.active_set == r['active_set'].tolist()
+            for fld in 'AbCd':
+                x = getattr(a, fld)
+                assert x.shape == r[fld].shape and x.dtype == numpy.float64 and x.flags.c_contiguous, fld
+                assert rel_err(x, r[fld]) <= REL_TOL, (name, a.active_set, fld)
+            if tw.t == 1:
+                assert a.E.dtype.kind == 'i' and a.E.tolist() == r['E'].tolist() and rel_err(a.f, r['f']) <= REL_TOL
+            else:
+                assert a.E.shape[1] == r['E'].shape[1] and a.f.shape[1] == 1 and a.E.flags.c_contiguous
+            for lst in (a.omega_set, a.lambda_set, a.regular_set[0], a.regular_set[1]):
+                assert all(type(v) is int for v in lst)
+            bad = index_lists_match(a, r, rows=b[2], flags=b[3], margins=b[5], k_act=k_act, n_eq=tw.n_eq, m=tw.m, one_d=tw.t == 1)
+            assert not bad, (name, a.active_set, bad)
+            if tw.t > 1:
+                u1, u2 = rows_match_as_sets(a.E, a.f, r['E'], r['f'])
+                assert not u1 and not u2, (name, a.active_set)
+            n_checked += 1
+    assert n_checked == len(ref)
+
+
+def test_region_assembly_skips_non_regions_and_handles_empty_input():
+    from ppopt_b200 import engine
+    from ppopt_b200.critical_region import CriticalRegion
+    eng = types.SimpleNamespace(n=3, t=2, n_eq=0, m=6, mi=6)
+    laws, rows = numpy.zeros((3, 5, 3)), numpy.zeros((3, 8, 3))
+    flags, info = numpy.zeros((3, 8), dtype=numpy.int32), numpy.zeros((3, 4))
+    info[1, 0] = -1.0   # singular KKT system
+    assert engine.build_regions(eng, CriticalRegion, [[0, 1]] * 3, 2, laws, rows, flags, info) == [None, None, None]
+    assert engine.build_regions(eng, CriticalRegion, [], 2, laws[:0], rows[:0], flags[:0], info[:0]) == []

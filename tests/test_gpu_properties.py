@@ -283,7 +283,8 @@ def test_constructor_presolve_matches_reference():
 
 def test_raw_to_solution_end_to_end():
     """raw data -> constructor presolve -> solve_mpqp: the whole user path without any reference code"""
-    from ppopt_b200 import MPQP_Program, mpqp_algorithm, problems, solve_mpqp
+    import problems
+    from ppopt_b200 import MPQP_Program, mpqp_algorithm, solve_mpqp
     d = problems.mpc_double_integrator(5)
     prog = MPQP_Program(d['A'], d['b'], d['c'], d['H'], d['Q'], d['A_t'], d['b_t'], d['F'], equality_indices=d['equality_indices'])
     sol = solve_mpqp(prog, mpqp_algorithm.combinatorial)

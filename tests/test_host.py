@@ -58,7 +58,8 @@ def test_combination_tester_semantics():
 
 
 def test_problem_builders_reproduce_reference_inputs():
-    from ppopt_b200 import problems
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import problems
     for name, build in problems.CONFIGS.items():
         g = numpy.load(os.path.join(GOLDEN, name + '.npz'))
         raw = build()
