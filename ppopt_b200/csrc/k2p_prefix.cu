@@ -161,7 +161,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
             __syncthreads();
             const int s1 = ctl.seg_end;
             for (int i = s0 + tid; i < s1; i += THREADS)
-                if (cab[i] & K2P_TODO) ctl.any = 1;
+                if (cab[i] & K2P_TODO) atomicOr(&ctl.any, 1);
             __syncthreads();
             const int any_todo = ctl.any;
             if (!any_todo) { s0 = s1; __syncthreads(); continue; }   // (ctl is rewritten at the top of the loop)
@@ -328,6 +328,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                     // convergence point of the groups, once per iteration (the step below is one instruction stream for all
                     // of them); it also orders the coefficient stores of the set-up before lane 0's first read-modify-write
                     if (__all_sync(PPG_FULL, drained)) break;
+                    __syncwarp();   // (votes do not order memory) coefficient stores of the set-up before the first RMW
                     if (have && mode == 0) {
                         int kmax = 0;
 #pragma unroll
@@ -392,6 +393,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                     unsigned want = __ballot_sync(PPG_FULL, have && mode != 0);
                     while (want) {
                         constexpr int RW = (LD + 31) / 32;
+                        __syncwarp();   // lane 0's coefficient read-modify-writes are visible to the whole warp
                         const int og = (__ffs((int)want) - 1) / LANES;
                         const int osrc = og * LANES;
                         want &= ~(((LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u)) << osrc);
@@ -408,7 +410,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                             const int r = rr * 32 + lane;
                             const double c = r < LD ? k2p_lds(ocoef + woff + rr * 256u) : 0.0;
                             tb[rr] = __ballot_sync(PPG_FULL, c != 0.0);
-                            s[rr] = k2p_lds(v0_sa + woff + rr * 256u);   // (beyond LD: in-bounds garbage, never used)
+                            s[rr] = r < LD ? k2p_lds(v0_sa + woff + rr * 256u) : 0.0;
                         }
                         double ua = k2p_lds(v0_sa + oa), ub = has_b ? k2p_lds(v0_sa + ob) : 0.0;
 #pragma unroll
@@ -420,7 +422,8 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                                 const double cj = k2p_lds(ocoef + jj * 8u);
                                 const unsigned rb = gp_sa + jj * ROWB;
 #pragma unroll
-                                for (int r2 = 0; r2 < RW; ++r2) s[r2] = fma(cj, k2p_lds(rb + woff + r2 * 256u), s[r2]);
+                                for (int r2 = 0; r2 < RW; ++r2)
+                                    if (r2 * 32 + lane < LD) s[r2] = fma(cj, k2p_lds(rb + woff + r2 * 256u), s[r2]);
                                 ua = fma(cj, k2p_lds(rb + oa), ua);
                                 ub = fma(cj, k2p_lds(rb + ob), ub);
                             }
@@ -433,7 +436,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
 #pragma unroll
                         for (int rr = 0; rr < RW; ++rr) {
                             const int r = rr * 32 + lane;
-                            s[rr] = fma(xa, k2p_lds(rpa + rr * 256u), fma(xb, k2p_lds(rpb + rr * 256u), s[rr]));
+                            if (r < LD) s[rr] = fma(xa, k2p_lds(rpa + rr * 256u), fma(xb, k2p_lds(rpb + rr * 256u), s[rr]));
                             const bool pk = (r < P.mi && ((pf0[(r >> 6) & 3] >> (r & 63)) & 1ull)) || (unsigned)r * 8u == oa ||
                                             (unsigned)r * 8u == ob;
                             if (r < R0) {
@@ -495,6 +498,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                             if (mine) have = false;
                         }
                         if (mine && !have) { n_it += (unsigned)nst; mode = 0; }
+                        __syncwarp();   // everybody is done reading the group's coefficients before its next set-up
                     }
                 }
             }

@@ -7,7 +7,7 @@ from enum import Enum
 
 import numpy
 
-from . import mpqp_combinatorial
+from . import mpqp_combi_graph, mpqp_combinatorial
 
 
 class mpqp_algorithm(Enum):
@@ -37,9 +37,12 @@ def solve_mpqp(problem, algorithm: mpqp_algorithm = mpqp_algorithm.combinatorial
         raise TypeError("You must pass an algorithm from mpqp_algorithm as the continuous algorithm. These can be found "
                         "by importing the following \n\nfrom ppopt_b200.mp_solvers.solve_mpqp import mpqp_algorithm\n\n"
                         f"With the following choices\n{mpqp_algorithm.all_algos()}")
-    if algorithm is not mpqp_algorithm.combinatorial:
-        raise NotImplementedError(f'{algorithm} is outside the scope of the B200 engine (combinatorial only)')
-    solution = mpqp_combinatorial.solve(problem)
+    if algorithm is mpqp_algorithm.combinatorial_graph:
+        solution = mpqp_combi_graph.solve(problem)          # solve_mpqp.py:100-101
+    elif algorithm is mpqp_algorithm.combinatorial:
+        solution = mpqp_combinatorial.solve(problem)        # solve_mpqp.py:70-71
+    else:
+        raise NotImplementedError(f'{algorithm} is outside the scope of the B200 engine (combinatorial, combinatorial_graph)')
     # overlap flags exactly as the reference sets them (solve_mpqp.py:105-112)
     if hasattr(problem, 'Q') and problem.Q is not None:
         if min(numpy.linalg.eigvalsh(problem.Q)) <= 0:

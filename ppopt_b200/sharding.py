@@ -75,8 +75,9 @@ def gather_regions(eng, mine: torch.Tensor, bufs, k_act: int, dist):
     parts.append(pad(mine, (), torch.int64))
     gathered = []
     for x in parts:
-        buf = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=dev)
+        buf = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)   # concatenated layout
         dist.all_gather_into_tensor(buf, x)
+        buf = buf.view((world,) + tuple(x.shape))
         gathered.append(torch.cat([buf[r, :counts_h[r]] for r in range(world)]))
     idx = gathered[4]
     order = torch.argsort(idx)

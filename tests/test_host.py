@@ -132,6 +132,28 @@ for lv in range(int(g['n_levels'])):
     mine = sharding.owned(idx, n, rank, world)
     allm = [None, None]; dist.all_gather_object(allm, mine.tolist())
     assert sorted(allm[0] + allm[1]) == idx.tolist()
+    # region payloads: every rank emits its own regions (CPU checker standing in for K5), the raw buffers are gathered
+    # through all_gather on padded tensors and must arrive complete, in candidate order, identical on both ranks
+    import types
+    k_act = cands.shape[1] - tw.n_eq
+    eng = types.SimpleNamespace(tdev=torch.device('cpu'), n=tw.n, n_eq=tw.n_eq, t=tw.t, R0=tw.R0)
+    bufs = None
+    if mine.shape[0]:
+        em = [tw.emit(tw.masks([cands[i].tolist()])[0]) for i in mine.tolist()]
+        bufs = [torch.from_numpy(numpy.stack([e[1] for e in em])), torch.from_numpy(numpy.stack([e[2] for e in em])),
+                torch.from_numpy(numpy.stack([e[3] for e in em])), torch.from_numpy(numpy.stack([e[4] for e in em]))]
+    gi, gb = sharding.gather_regions(eng, mine, bufs, k_act, dist)
+    assert gi.tolist() == idx.tolist(), (rank, lv)
+    if idx.shape[0]:
+        ref = [tw.emit(tw.masks([cands[i].tolist()])[0]) for i in idx.tolist()]
+        for j in range(4):
+            assert numpy.array_equal(gb[j].numpy(), numpy.stack([e[j + 1] for e in ref])), (rank, lv, j)
+        st2 = sharding.gather_region_bits(full.clone() & 7, gi, dist, already_global=True, bufs=gb)
+        assert numpy.array_equal(st2.numpy() & 8, full.numpy() & 8)
+    bits_in = (full & 7).clone()
+    bits_in[mine] |= 8
+    st3 = sharding.gather_region_bits(bits_in, mine, dist)
+    assert numpy.array_equal(st3.numpy() & 8, full.numpy() & 8)
 dist.barrier(); dist.destroy_process_group()
 print('ok', rank)
 '''
@@ -139,7 +161,8 @@ print('ok', rank)
 
 def test_level_sharding_world_size_2_gloo(tmp_path):
     """N>1 host path on CPU: each rank evaluates its chunks (CPU checker standing in for the kernels), status bytes
-    are all-reduced over gloo, every rank ends with the reference's full status vector."""
+    are all-reduced over gloo, every rank ends with the reference's full status vector; the region payloads of the
+    owning ranks are gathered as raw buffers (sharding.gather_regions) and the region bits made global."""
     script = tmp_path / 'worker.py'
     script.write_text(WORKER)
     port = str(29500 + os.getpid() % 2000)
