@@ -36,7 +36,7 @@ constexpr double K2P_OMEGA = 1.35, K2P_OMEGA2 = 1.8;   // see k2a_relax.cu (scan
 constexpr int K2P_STALL1 = 16, K2P_STALL2 = 48;
 constexpr unsigned K2P_TODO = 1u << 16;
 
-struct K2pCtl { long long base; int next; int seg_end; int any; int valid; };
+struct K2pCtl { long long base; unsigned long long pf[4]; unsigned long long n_try, n_ok, n_it; int next; int seg_end; int any; int valid; };
 
 __device__ __forceinline__ double k2p_lds(unsigned a) {
     double x;
@@ -79,6 +79,24 @@ __device__ __forceinline__ int k2p_nth(const uint64_t (&m)[4], int j) {
     return r;
 }
 
+// max of `key` over each group of LANES lanes, on every lane of the group: one redux.sync per group (the whole warp takes
+// part, lanes of the other groups contribute INT_MIN) - a 4-step shuffle ladder is ~110 cycles of dependent latency, 32 / LANES
+// independent redux instructions ~30
+template <int LANES>
+__device__ __forceinline__ int k2p_group_max(int key, int g) {
+    if constexpr (LANES == 32) {
+        return __reduce_max_sync(PPG_FULL, key);
+    } else {
+        int out = 0;
+#pragma unroll
+        for (int q = 0; q < 32 / LANES; ++q) {
+            const int m = __reduce_max_sync(PPG_FULL, g == q ? key : (int)0x80000000);
+            if (g == q) out = m;
+        }
+        return out;
+    }
+}
+
 template <int LANES, int RL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
@@ -117,7 +135,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
     int kid[RL];
 #pragma unroll
     for (int rr = 0; rr < RL; ++rr) { kid[rr] = rr * LANES + gl; asm volatile("" : "+r"(kid[rr])); }
-    unsigned long long n_try = 0, n_ok = 0, n_it = 0;
+    if (tid == 0) { ctl.n_try = 0ull; ctl.n_ok = 0ull; ctl.n_it = 0ull; }
 
     for (;;) {
         __syncthreads();   // everybody is done with the previous chunk (ctl, cmask, cab)
@@ -150,7 +168,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
             // ---- segment [s0, s1): candidates with the prefix of candidate s0
             uint64_t pf0[4];
             k2p_prefix_words(cmask + (size_t)s0 * W, W, k_act >= 1 ? cab[s0] : 0xffffu, pf0);
-            if (tid == 0) { ctl.seg_end = cn; ctl.any = 0; ctl.valid = 1; }
+            if (tid == 0) { ctl.seg_end = cn; ctl.any = 0; ctl.valid = 1; ctl.pf[0] = pf0[0]; ctl.pf[1] = pf0[1]; ctl.pf[2] = pf0[2]; ctl.pf[3] = pf0[3]; }
             __syncthreads();
             for (int i = s0 + 1 + tid; i < cn; i += THREADS) {
                 uint64_t pf[4];
@@ -254,28 +272,22 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
 
             // ---- candidates of the segment: every group pulls one after the other
             if (valid) {
-                // rows of this lane that are parked for the whole segment: prefix rows and the padding beyond R0
-                unsigned ppark = 0;
-#pragma unroll
-                for (int rr = 0; rr < RL; ++rr) {
-                    const int r = rr * LANES + gl;
-                    const bool pk = r >= R0 || (r < P.mi && ((pf0[(r >> 6) & 3] >> (r & 63)) & 1ull));
-                    ppark |= (pk ? 1u : 0u) << rr;
-                }
                 bool have = false, drained = false;
                 int mode = 0;            // 0 stepping, 1 converged (verify), 2 giving up (hand over)
-                long long idx = 0;
-                unsigned cw = 0;         // staged word of the current candidate
+                int ci = 0;              // position of the current candidate in the staged chunk
+                unsigned cw = 0;         // its staged word
                 unsigned a_off = 0, b_off = 0, park = 0;
                 double i11 = 0.0, i12 = 0.0, i22 = 0.0;
                 double v[RL], ca[RL], cb[RL];
-                double omega = K2P_OMEGA;
-                int left = 0, chk = 0, wref = 0, rechecks = 0, nst = 0, wkey = 0;
-                bool second = false, first = true;
+                int it = 0, it_evt = 0, it_end = 0, next_chk = 0, wref = 0, rechecks = 0, nst = 0;
+                bool second = false;
+                const bool lead = lane_off == 0u;   // lane 0 of the group
+                // which lanes report what in the one vote of an iteration: lane 0 of a group "wants a verification",
+                // lane 1 "drained"
+                constexpr unsigned LEADS = LANES == 32 ? 1u : (LANES == 16 ? 0x00010001u : 0x01010101u);
                 for (;;) {
                     if (!have && !drained) {
-                        int ci = 0;
-                        if (gl == 0) {
+                        if (lead) {
                             unsigned w;
                             do {
                                 ci = atomicAdd(&ctl.next, 1);
@@ -288,8 +300,6 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                         } else {
                             // ---- set-up: the candidate's own two rows, start point = min-norm point of its equalities
                             cw = k2p_ldsu(cab_sa + 4u * (unsigned)ci);
-                            idx = base + ci;
-                            ++n_try;
                             const unsigned a_row = cw & 255u, b_row = (cw >> 8) & 255u;
                             a_off = a_row * 8u; b_off = b_row * 8u;
                             const unsigned rpa = gp_sa + a_row * ROWB, rpb = gp_sa + b_row * ROWB;
@@ -297,6 +307,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                             const double s12 = has_b ? k2p_lds(rpa + b_off) : 0.0;
                             const double s22 = has_b ? k2p_lds(rpb + b_off) : 1.0;
                             const double det = fma(s11, s22, -s12 * s12);
+                            if (lead) atomicAdd(&ctl.n_try, 1ull);
                             if (s11 > 1e-12 && s22 > 1e-12 && det > 1e-12 * s11 * s22) {   // else: left to the simplex
                                 double dinv;
                                 asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(dinv) : "d"(det));
@@ -305,98 +316,107 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                                 i11 = s22 * dinv; i12 = -s12 * dinv; i22 = has_b ? s11 * dinv : 0.0;
                                 const double va = k2p_lds(v0_sa + a_off), vb = has_b ? k2p_lds(v0_sa + b_off) : 0.0;
                                 const double xa = fma(i11, va, i12 * vb), xb = fma(i12, va, i22 * vb);
-                                park = ppark;
+                                park = 0;
 #pragma unroll
                                 for (int rr = 0; rr < RL; ++rr) {
                                     const unsigned o = lane_off + rr * SLOTB;
+                                    const int r = kid[rr];
                                     ca[rr] = k2p_lds(rpa + o);
                                     cb[rr] = has_b ? k2p_lds(rpb + o) : 0.0;
-                                    if (kid[rr] == (int)a_row || kid[rr] == (int)b_row) park |= 1u << rr;
+                                    // parked rows: the prefix (segment-wide), the candidate's own two, the padding beyond R0
+                                    const bool pk = r >= R0 || r == (int)a_row || r == (int)b_row ||
+                                                    (r < P.mi && ((ctl.pf[(r >> 6) & 3] >> (r & 63)) & 1ull));
+                                    park |= (pk ? 1u : 0u) << rr;
                                     const double s = fma(-xb, cb[rr], fma(-xa, ca[rr], k2p_lds(v0_sa + o)));
-                                    v[rr] = ((park >> rr) & 1u) ? -1e300 : s;   // parked: never the maximum
+                                    v[rr] = pk ? -1e300 : s;   // parked: never the maximum
                                     k2p_sts(coef_sa + o, 0.0);
                                 }
-                                omega = K2P_OMEGA;
-                                left = max_iter; chk = 0; wref = 0; rechecks = 0; nst = 0;
+                                it = 0; it_end = max_iter; next_chk = 0; it_evt = 0; wref = 0; rechecks = 0; nst = 0;
                                 second = max_iter2 <= 0;
-                                first = true;
                                 mode = 0;
                                 have = true;
                             }
                         }
                     }
-                    // convergence point of the groups, once per iteration (the step below is one instruction stream for all
-                    // of them); it also orders the coefficient stores of the set-up before lane 0's first read-modify-write
-                    if (__all_sync(PPG_FULL, drained)) break;
-                    __syncwarp();   // (votes do not order memory) coefficient stores of the set-up before the first RMW
-                    if (have && mode == 0) {
-                        int kmax = 0;
+                    // ---- the one convergence point of an iteration: the groups vote (and the barrier orders the coefficient
+                    // stores of a set-up before the first read-modify-write)
+                    __syncwarp();
+                    // ---- most violated row of every group: arg-max over keys = high word of the residual with the row index
+                    // in its 7 low bits.  Every lane takes part (full-mask shuffles; the ladder never leaves a group), groups
+                    // that are not stepping carry a harmless key and their updates below are switched off by tau = 0.
+                    const bool stepping = have && mode == 0;
+                    int kmax = 0;
 #pragma unroll
-                        for (int rr = 0; rr < RL; ++rr) kmax = max(kmax, (__double2hiint(v[rr]) & ~127) | kid[rr]);
+                    for (int rr = 0; rr < RL; ++rr) kmax = max(kmax, (__double2hiint(v[rr]) & ~127) | kid[rr]);
 #pragma unroll
-                        for (int o = LANES / 2; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(gmask, kmax, o));
-                        wkey = kmax;
-                        if (wkey <= ktol) {
-                            mode = 1;
-                        } else if (min(chk, left) <= 0) {
+                    for (int o = LANES / 2; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(PPG_FULL, kmax, o));
+                    const int wkey = kmax;
+                    bool go = stepping && wkey > ktol;
+                    if (stepping) {
+                        if (wkey <= ktol) mode = 1;
+                        if (go && it >= it_evt) {
                             // stall detector (see k2a_relax.cu): not halving the worst violation in 16 steps -> longer
-                            // stride, then the simplex
-                            bool stalled = left <= 0;
+                            // stride, then the simplex.  Visited every 16 / 48 steps and at the end of a budget.
+                            bool stalled = it >= it_end;
                             if (!stalled) {
-                                stalled = !first && wkey > wref - 0x100000;
+                                stalled = it != 0 && wkey > wref - 0x100000;
                                 wref = wkey;
-                                chk = second ? K2P_STALL2 : K2P_STALL1;
+                                next_chk = it + (second ? K2P_STALL2 : K2P_STALL1);
                             }
                             if (stalled) {
                                 if (second) {
                                     mode = 2;
+                                    go = false;
                                 } else {
                                     second = true;
-                                    omega = K2P_OMEGA2;
-                                    left = max_iter2;
+                                    it_end = it + max_iter2;
                                     wref = wkey;
-                                    chk = K2P_STALL2;
+                                    next_chk = it + K2P_STALL2;
                                 }
                             }
+                            it_evt = min(it_end, next_chk);
                         }
-                        first = false;
-                        --chk;
-                        --left;
+                        ++it;
                     }
-                    if (have && mode == 0) {
-                        // ---- one relaxation step along row j inside the subspace of the active rows
-                        const unsigned j = (unsigned)wkey & 127u;
+                    {
+                        // ---- one relaxation step along row j inside the subspace of the active rows (no branch: a group
+                        // that is not stepping runs it with tau = 0 and writes nothing)
+                        const unsigned j = stepping ? ((unsigned)wkey & 127u) : 0u;   // (idle groups: a valid row, results unused)
                         const unsigned rowb = gp_sa + j * ROWB;
+                        const unsigned rowl = rowb + lane_off;
                         const double ga = k2p_lds(rowb + a_off), gb = k2p_lds(rowb + b_off), gjj = k2p_lds(rowb + j * 8u);
+                        const double cold = lead ? k2p_lds(coef_sa + j * 8u) : 0.0;   // (issued early: its latency overlaps the step)
                         const double m0 = fma(ga, i11, gb * i12), m1 = fma(ga, i12, gb * i22);
                         const double nn = fma(-m1, gb, fma(-m0, ga, gjj));   // |N g_j|^2
-                        if (!(nn > 1e-12)) {
-                            mode = 2;   // row j lies in the span of the active rows: leave it to the LP
-                        } else {
-                            const double wmax = __hiloint2double(wkey & ~127, 0);   // its violation, rounded down by < 2^-13
-                            double rnn;
-                            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rnn) : "d"(nn));
-                            const double tau = (omega * wmax) * rnn;
-                            const double t0 = tau * m0, t1 = tau * m1;
-                            const unsigned rowl = rowb + lane_off;
+                        const bool okn = nn > 1e-12;
+                        if (go && !okn) mode = 2;   // row j lies in the span of the active rows: leave it to the LP
+                        go = go && okn;
+                        const double wmax = __hiloint2double(wkey & ~127, 0);   // its violation, rounded down by < 2^-13
+                        double rnn;
+                        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rnn) : "d"(nn));
+                        double tau = ((second ? K2P_OMEGA2 : K2P_OMEGA) * wmax) * rnn;
+                        tau = go ? tau : 0.0;
+                        const double t0 = tau * m0, t1 = tau * m1;
 #pragma unroll
-                            for (int rr = 0; rr < RL; ++rr) {
-                                const double x = k2p_lds(rowl + rr * SLOTB);
-                                v[rr] = fma(t1, cb[rr], fma(t0, ca[rr], fma(-tau, x, v[rr])));
-                            }
-                            if (gl == 0) k2p_sts(coef_sa + j * 8u, k2p_lds(coef_sa + j * 8u) - tau);
-                            ++nst;
+                        for (int rr = 0; rr < RL; ++rr) {
+                            const double x = k2p_lds(rowl + rr * SLOTB);
+                            v[rr] = fma(t1, cb[rr], fma(t0, ca[rr], fma(-tau, x, v[rr])));
                         }
+                        if (go && lead) k2p_sts(coef_sa + j * 8u, cold - tau);
+                        nst += go ? 1 : 0;
                     }
+                    // one vote: lane 0 of every group reports "wants a verification", lane 1 "drained"
+                    const unsigned bal = __ballot_sync(PPG_FULL, lead ? (have && mode != 0) : drained);
+                    if (((bal >> 1) & LEADS) == LEADS) break;
+                    unsigned want = bal & LEADS;
                     // ---- verification / hand-over, one group at a time with the WHOLE warp doing the arithmetic:
                     // exact residuals of the group's current point from its coefficients, all rows (32 lanes x RW rows)
-                    unsigned want = __ballot_sync(PPG_FULL, have && mode != 0);
                     while (want) {
                         constexpr int RW = (LD + 31) / 32;
                         __syncwarp();   // lane 0's coefficient read-modify-writes are visible to the whole warp
                         const int og = (__ffs((int)want) - 1) / LANES;
                         const int osrc = og * LANES;
-                        want &= ~(((LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u)) << osrc);
+                        want &= want - 1u;
                         const bool mine = g == og;
                         const unsigned oa = __shfl_sync(PPG_FULL, a_off, osrc), ob = __shfl_sync(PPG_FULL, b_off, osrc);
                         const double o11 = shfl_d(i11, osrc), o12 = shfl_d(i12, osrc), o22 = shfl_d(i22, osrc);
@@ -421,11 +441,14 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                                 bits &= bits - 1u;
                                 const double cj = k2p_lds(ocoef + jj * 8u);
                                 const unsigned rb = gp_sa + jj * ROWB;
+                                double gx[RW];
 #pragma unroll
-                                for (int r2 = 0; r2 < RW; ++r2)
-                                    if (r2 * 32 + lane < LD) s[r2] = fma(cj, k2p_lds(rb + woff + r2 * 256u), s[r2]);
-                                ua = fma(cj, k2p_lds(rb + oa), ua);
-                                ub = fma(cj, k2p_lds(rb + ob), ub);
+                                for (int r2 = 0; r2 < RW; ++r2) gx[r2] = r2 * 32 + lane < LD ? k2p_lds(rb + woff + r2 * 256u) : 0.0;
+                                const double gxa = k2p_lds(rb + oa), gxb = k2p_lds(rb + ob);
+#pragma unroll
+                                for (int r2 = 0; r2 < RW; ++r2) s[r2] = fma(cj, gx[r2], s[r2]);
+                                ua = fma(cj, gxa, ua);
+                                ub = fma(cj, gxb, ub);
                             }
                         }
                         if (!has_b) ub = 0.0;
@@ -437,7 +460,7 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                         for (int rr = 0; rr < RW; ++rr) {
                             const int r = rr * 32 + lane;
                             if (r < LD) s[rr] = fma(xa, k2p_lds(rpa + rr * 256u), fma(xb, k2p_lds(rpb + rr * 256u), s[rr]));
-                            const bool pk = (r < P.mi && ((pf0[(r >> 6) & 3] >> (r & 63)) & 1ull)) || (unsigned)r * 8u == oa ||
+                            const bool pk = (r < P.mi && ((ctl.pf[(r >> 6) & 3] >> (r & 63)) & 1ull)) || (unsigned)r * 8u == oa ||
                                             (unsigned)r * 8u == ob;
                             if (r < R0) {
                                 worst = fmax(worst, pk ? fabs(s[rr]) : s[rr]);
@@ -462,11 +485,11 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                             const int rc = __shfl_sync(PPG_FULL, rechecks, osrc);
                             again = rc < 3;
                         }
+                        const long long oidx = ctl.base + __shfl_sync(PPG_FULL, ci, osrc);
+                        const uint8_t ost = (uint8_t)(__shfl_sync(PPG_FULL, cw, osrc) >> 24);
                         if (pass) {
-                            if (mine) {
-                                if (gl == 0) { ++n_ok; status[idx] = (uint8_t)(cw >> 24) | PPG_ST_FEAS; }
-                                have = false;
-                            }
+                            if (lane == 0) { atomicAdd(&ctl.n_ok, 1ull); status[oidx] = ost | PPG_ST_FEAS; }
+                            if (mine) have = false;
                         } else if (again) {
                             double* vs = scr_v + (size_t)warp * (RW * 32);
 #pragma unroll
@@ -489,15 +512,18 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
 #pragma unroll
                                     for (int rr = 0; rr < RW; ++rr)
                                         if (fin && rr * 32 + lane < R0) P.warm_resid[slot * (unsigned long long)R0 + rr * 32 + lane] = s[rr];
-                                    if (mine && gl == 0) {
-                                        P.warm_idx[slot] = fin ? idx : -1;
-                                        if (fin) status[idx] = (uint8_t)(cw >> 24) | PPG_ST_PRE;
+                                    if (lane == 0) {
+                                        P.warm_idx[slot] = fin ? oidx : -1;
+                                        if (fin) status[oidx] = ost | PPG_ST_PRE;
                                     }
                                 }
                             }
                             if (mine) have = false;
                         }
-                        if (mine && !have) { n_it += (unsigned)nst; mode = 0; }
+                        if (mine && !have) {
+                            if (gl == 0) atomicAdd(&ctl.n_it, (unsigned long long)nst);
+                            mode = 0;
+                        }
                         __syncwarp();   // everybody is done reading the group's coefficients before its next set-up
                     }
                 }
@@ -506,11 +532,12 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
             __syncthreads();   // the segment's Gp and coefficient vectors are no longer read
         }
     }
-    if (gl == 0 && n_try) {
-        atomicAdd(&counters[CNT_K2A_TRIED], n_try);
-        atomicAdd(&counters[CNT_K2A_CERTIFIED], n_ok);
-        atomicAdd(&counters[CNT_K2A_STEPS], n_it);
-        atomicAdd(&counters[CNT_K2A_WORK], n_it * (unsigned long long)(R0 * (has_b ? 3 : 2)));
+    __syncthreads();
+    if (tid == 0 && ctl.n_try) {
+        atomicAdd(&counters[CNT_K2A_TRIED], ctl.n_try);
+        atomicAdd(&counters[CNT_K2A_CERTIFIED], ctl.n_ok);
+        atomicAdd(&counters[CNT_K2A_STEPS], ctl.n_it);
+        atomicAdd(&counters[CNT_K2A_WORK], ctl.n_it * (unsigned long long)(R0 * (has_b ? 3 : 2)));
     }
 }
 
@@ -559,7 +586,10 @@ cudaError_t launch_k2a_prefix(const DevProgram& P, const uint64_t* masks, long l
 #define K2P_GO(L, R, T) return launch_k2p_t<L, R, T>(P, masks, n, k_act, status, queue, counters, max_iter, sm_count, st, handled)
     // 16 lanes x RL rows per candidate, 512 threads: measured best on the 100x30x6 program (8 lanes x 14 rows: fewer
     // instructions per candidate but 10 warps per SM hide less latency, 546 vs 488 ms; 640+ threads spill)
+    static const int thr = getenv("PPGPU_K2P_THREADS") ? atoi(getenv("PPGPU_K2P_THREADS")) : 512;
     const int rh = (P.R0 + 15) / 16;
+    if (rh == 7 && thr == 640) K2P_GO(16, 7, 640);
+    if (rh == 7 && thr == 768) K2P_GO(16, 7, 768);
     switch (rh) {
         case 1: K2P_GO(16, 1, 512);
         case 2: K2P_GO(16, 2, 512);

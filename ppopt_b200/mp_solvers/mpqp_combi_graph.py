@@ -45,7 +45,7 @@ def _seed(program, eng) -> List[tuple]:
 
 def solve(program, initial_active_sets: Optional[Iterable] = None, return_trace: bool = False):
     """Solves the mpQP with the combinatorial connected-graph algorithm; Solution as the reference's (region order is
-    arbitrary there).  ``return_trace``: also return {active set: (full_rank, non_empty, region)} for every visited set."""
+    arbitrary there).  ``return_trace``: also return {active set: (full_rank, non_empty, region, thin_only)} for every visited set."""
     eng = _engine.Engine(_engine.program_arrays(program))
     try:
         if not (eng.is_qp and eng.use_gram):
@@ -70,6 +70,14 @@ def solve(program, initial_active_sets: Optional[Iterable] = None, return_trace:
                     nxt.append(a_)
             for k_act in sorted(by_k):
                 sets = by_k[k_act]
+                if k_act > eng.n - n_eq:
+                    # more active rows than variables: rank deficient by counting (is_full_rank compares rank with len(A))
+                    for a in sets:
+                        trace[a] = (False, False, False, False)
+                        for i in a:
+                            if i not in eq:
+                                push(tuple(x for x in a if x != i))
+                    continue
                 masks = eng.masks_from_lists(sets)
                 status = eng.level_eval(masks, k_act, stages=1)                       # is_full_rank
                 full = (status & ST_RANK) != 0
@@ -90,7 +98,9 @@ def solve(program, initial_active_sets: Optional[Iterable] = None, return_trace:
                 for a, s_ in zip(sets, st):
                     rank_ok = bool(s_ & ST_RANK)
                     nonempty = rank_ok and bool(s_ & (ST_OPT | ST_THIN))
-                    trace[a] = (rank_ok, nonempty, a in built)
+                    # 4th entry: non-empty only by the LP tolerance band (radius in [-1e-7, 0.5e-8)): the reference's LP, run on
+                    # UN-normalised rows, may call such a polytope empty
+                    trace[a] = (rank_ok, nonempty, a in built, bool(s_ & ST_THIN) and not bool(s_ & ST_OPT))
                     if a in built:
                         regions.append(built[a])
                     if (not rank_ok) or nonempty:
