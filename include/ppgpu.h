@@ -44,7 +44,7 @@ typedef struct {
     int32_t max_depth;    /* max(n, t) - n_eq   mpqp_combinatorial.py:24 */
     int32_t sm_count;
     int32_t lp_columns;   /* padded register columns of the feasibility tableau */
-    int32_t reserved;
+    int32_t reserved;     /* 1: the vertex walk (K2w) has a start vertex for this program */
 } ppgpu_info;
 
 /* number of uint64 counters returned by ppgpu_counters */
@@ -61,6 +61,13 @@ int ppgpu_program_create(const ppgpu_dims* dims, const double* h_A, const double
                          const double* h_H, int device, ppgpu_program** out);
 int ppgpu_program_destroy(ppgpu_program* prog);
 int ppgpu_program_info(const ppgpu_program* prog, ppgpu_info* out);
+
+/* Engine knobs of one handle (no reference counterpart: the reference has one LP call per candidate and nothing to tune).
+ *   PPGPU_OPT_K2W_MIN  smallest number of candidates per ppgpu_level_eval chunk for which the feasibility certificates are
+ *                      produced by the vertex walk (csrc/k2w_walk.cu) before the relaxation (default 500000; 0: always;
+ *                      negative: never).  Decisions do not depend on it - only which kernel exhibits the feasible point. */
+#define PPGPU_OPT_K2W_MIN 0
+int ppgpu_set_option(ppgpu_program* prog, int32_t option, int64_t value);
 
 /* Level-1 candidates = generate_children_sets(equality_indices, m, murder_list) (solver_utils.py:154-166) plus the mpLP
  * cardinality filter (mpqp_combinatorial.py:40-42).  d_masks must hold n_ineq x words uint64. */
@@ -138,8 +145,9 @@ int64_t ppgpu_launch_count(const ppgpu_program* prog);
 
 /* Optional per-kernel-family timing with CUDA events recorded on the launch stream (used by bench.py for the
  * roofline line).  Families: 0 K1 rank, 1 K2 feasibility LP, 2 K3/K4 screen, 3 K5 emission, 4 K6 count, 5 K6 write,
- * 6 ordered compaction, 7 K2a relaxation certificates.  h_ms / h_launches hold PPGPU_NUM_FAMILIES entries. */
-#define PPGPU_NUM_FAMILIES 8
+ * 6 ordered compaction, 7 K2a relaxation certificates, 8 K2w vertex-walk certificates.  h_ms / h_launches hold
+ * PPGPU_NUM_FAMILIES entries. */
+#define PPGPU_NUM_FAMILIES 9
 int ppgpu_profile_enable(ppgpu_program* prog, int32_t on);
 int ppgpu_profile_read(ppgpu_program* prog, double* h_ms, int64_t* h_launches, int32_t reset);
 

@@ -810,6 +810,16 @@ int twin_feas_rhs(void* h, const int* act, int k, const double* rhs, int* pivots
     if (res.code == PPG_LP_OPTIMAL) return res.beta >= -PPG_FEAS_TOL;
     return 0;
 }
+// K2w start vertex (host_math.hpp::build_walk_dictionary): returns wk_ok; D0 (nb x ld), bvar (nb), nvar (nfree) when ok
+int twin_walk_dict(void* h, int* nb, int* ld, double* D0, int* bvar, int* nvar) {
+    const ReducedProgram& P = ((Twin*)h)->P;
+    *nb = P.wk_nb; *ld = P.wk_ld;
+    if (!P.wk_ok) return 0;
+    if (D0) std::memcpy(D0, P.wk_D0.data(), P.wk_D0.size() * sizeof(double));
+    if (bvar) std::memcpy(bvar, P.wk_bvar.data(), P.wk_bvar.size() * sizeof(int));
+    if (nvar) std::memcpy(nvar, P.wk_nvar.data(), P.wk_nvar.size() * sizeof(int));
+    return 1;
+}
 int twin_rows(void* h) { return ((Twin*)h)->P.R0; }
 int twin_nfree(void* h) { return ((Twin*)h)->P.nfree; }
 void twin_t0(void* h, double* out) {

@@ -108,6 +108,24 @@ class Twin:
         f = lib().twin_feas_rhs(self.h, act.ctypes.data, len(act), None if r is None else r.ctypes.data, ctypes.byref(piv))
         return bool(f), piv.value
 
+    def walk_dict(self):
+        """start vertex of the K2w walk: (D0 [beta | D], basic rows, nonbasic rows, T0) or None when the program has none"""
+        l = lib()
+        l.twin_walk_dict.argtypes = [ctypes.c_void_p] * 6
+        l.twin_nfree.argtypes = [ctypes.c_void_p]
+        l.twin_rows.argtypes = [ctypes.c_void_p]
+        l.twin_t0.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        nb, ld = ctypes.c_int(0), ctypes.c_int(0)
+        if not l.twin_walk_dict(self.h, ctypes.byref(nb), ctypes.byref(ld), None, None, None):
+            return None
+        nf, R0 = l.twin_nfree(self.h), l.twin_rows(self.h)
+        D0 = numpy.zeros((nb.value, ld.value))
+        bvar, nvar = numpy.zeros(nb.value, dtype=numpy.int32), numpy.zeros(nf, dtype=numpy.int32)
+        l.twin_walk_dict(self.h, ctypes.byref(nb), ctypes.byref(ld), D0.ctypes.data, bvar.ctypes.data, nvar.ctypes.data)
+        T0 = numpy.zeros((R0, nf + 2))
+        l.twin_t0(self.h, T0.ctypes.data)
+        return D0, bvar, nvar, T0
+
     def pivots(self):
         return lib().twin_pivots(self.h)
 

@@ -7,13 +7,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libppgpu.so')
 
 NUM_COUNTERS = 24
-NUM_FAMILIES = 8
-FAMILY_NAMES = ('k1_rank', 'k2_feas_lp', 'k34_kkt_cheb', 'k5_emit', 'k6_count', 'k6_write', 'select', 'k2a_relax')
+NUM_FAMILIES = 9
+FAMILY_NAMES = ('k1_rank', 'k2_feas_lp', 'k34_kkt_cheb', 'k5_emit', 'k6_count', 'k6_write', 'select', 'k2a_relax', 'k2w_walk')
 COUNTER_NAMES = ('k1_candidates', 'k2_lps', 'k2_pivots', 'k2_work', 'k4_lps', 'k4_pivots', 'k4_work', 'k5_lps',
-                 'k5_pivots', 'k5_work', 'numeric', 'border', 'k6_lookups', 'k2a_tried', 'k2a_certified', 'k2a_steps', 'k2a_work')
+                 'k5_pivots', 'k5_work', 'numeric', 'border', 'k6_lookups', 'k2a_tried', 'k2a_certified', 'k2a_steps', 'k2a_work',
+                 'k2w_certified', 'k2w_pivots', 'k2w_work', 'k2w_giveup')
 
 # status bits (csrc/tolerances.h)
 ST_RANK, ST_FEAS, ST_OPT, ST_REGION, ST_BORDER, ST_NUMERIC, ST_THIN = 1, 2, 4, 8, 16, 32, 64
+OPT_K2W_MIN = 0   # ppgpu_set_option (include/ppgpu.h)
 
 
 class Dims(ctypes.Structure):
@@ -33,6 +35,7 @@ SYMBOLS = {
     'ppgpu_program_create': (ctypes.c_int, [ctypes.POINTER(Dims)] + [_vp] * 8 + [ctypes.c_int, ctypes.POINTER(_vp)]),
     'ppgpu_program_destroy': (ctypes.c_int, [_vp]),
     'ppgpu_program_info': (ctypes.c_int, [_vp, ctypes.POINTER(Info)]),
+    'ppgpu_set_option': (ctypes.c_int, [_vp, _i32, _i64]),
     'ppgpu_root_level': (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_i64), _vp]),
     'ppgpu_level_eval': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
     'ppgpu_scan_workspace_bytes': (_sz, [_i64]),

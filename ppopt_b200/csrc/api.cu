@@ -35,6 +35,7 @@ struct ppgpu_program {
     double* d_warm_resid = nullptr;
     long long* d_warm_idx = nullptr;
     unsigned long long* d_warm_count = nullptr;
+    long long k2w_min = 500000;   // smallest launch the vertex walk (K2w) is used for (ppgpu_set_option)
     double prof_ms[PPGPU_NUM_FAMILIES] = {0};
     long long prof_launches[PPGPU_NUM_FAMILIES] = {0};
 };
@@ -116,6 +117,11 @@ int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, 
 #define UP(field, vecname) if ((e = upload(p, R.vecname, &D.field)) != cudaSuccess) { ppgpu_program_destroy(p); return fail("upload " #field, e); }
     UP(At, At) UP(C1, C1) UP(T0, T0) UP(Gam, Gam) UP(G, G) UP(V, V) UP(th_lo, th_lo) UP(th_hi, th_hi) UP(A, A) UP(b, b) UP(F, F) UP(A_t, At_theta) UP(b_t, bt) UP(Q, Q) UP(c, c) UP(H, H)
 #undef UP
+    D.wk_ok = R.wk_ok; D.wk_nb = R.wk_nb; D.wk_ld = R.wk_ld; D.wk_D0 = nullptr; D.wk_bvar = nullptr; D.wk_nvar = nullptr;
+    if (R.wk_ok) {
+        if ((e = upload(p, R.wk_D0, &D.wk_D0)) != cudaSuccess || (e = upload(p, R.wk_bvar, &D.wk_bvar)) != cudaSuccess ||
+            (e = upload(p, R.wk_nvar, &D.wk_nvar)) != cudaSuccess) { ppgpu_program_destroy(p); return fail("upload walk dictionary", e); }
+    }
     void* dc = nullptr;
     if ((e = cudaMalloc(&dc, (CNT_COUNT + QUEUE_SLOTS) * sizeof(unsigned long long))) != cudaSuccess) {
         ppgpu_program_destroy(p);
@@ -139,6 +145,14 @@ int ppgpu_program_destroy(ppgpu_program* p) {
     return 0;
 }
 
+int ppgpu_set_option(ppgpu_program* p, int32_t option, int64_t value) {
+    if (!p) return fail_msg("null argument");
+    switch (option) {
+        case PPGPU_OPT_K2W_MIN: p->k2w_min = value; return 0;
+        default: return fail_msg("unknown option");
+    }
+}
+
 int ppgpu_program_info(const ppgpu_program* p, ppgpu_info* o) {
     if (!p || !o) return fail_msg("null argument");
     const ReducedProgram& R = p->host;
@@ -146,7 +160,7 @@ int ppgpu_program_info(const ppgpu_program* p, ppgpu_info* o) {
     o->max_depth = (R.n > R.t ? R.n : R.t) - R.ne;
     o->sm_count = p->sm_count;
     o->lp_columns = k2_pad_columns(R.nfree + 2);
-    o->reserved = 0;
+    o->reserved = R.wk_ok;
     return 0;
 }
 
@@ -229,6 +243,14 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
     }
     static const int warm_on = getenv("PPGPU_WARM") ? atoi(getenv("PPGPU_WARM")) : 1;
     p->dev.warm_count = nullptr; p->dev.warm_resid = nullptr; p->dev.warm_idx = nullptr; p->dev.warm_cap = 0;
+    if ((stages & 2) && !(stages & 8) && k_act >= 1 && p->k2w_min >= 0 && n >= p->k2w_min) {
+        // certificates shared between the candidates of a prefix (vertex walk); the relaxation only sees what is left
+        ProfScope ps(p, st, 8);
+        bool handled = false;
+        e = launch_k2w(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st, &handled);
+        if (e != cudaSuccess) return fail("K2w vertex walk", e);
+        if (handled) p->launches++;
+    }
     if ((stages & 2) && !(stages & 8)) {
         // feasibility certificates first (cheap); the simplex only sees what is left, and starts from K2a's last iterate
         ProfScope ps(p, st, 7);

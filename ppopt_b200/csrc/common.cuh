@@ -29,6 +29,11 @@ struct DevProgram {
     long long* warm_idx;              // warm_cap candidate indices
     unsigned long long* warm_count;   // slots handed out (may exceed warm_cap: the overflow goes the cold way)
     long long warm_cap;
+    // K2w: slack dictionary of one feasible vertex of the feasibility polyhedron (host_math.hpp::build_walk_dictionary)
+    int wk_ok, wk_nb, wk_ld;
+    const double* wk_D0;   // wk_nb x wk_ld  [beta | D]
+    const int* wk_bvar;    // wk_nb  row (slack) basic in every dictionary row
+    const int* wk_nvar;    // nfree  row (slack) nonbasic in every column
 };
 
 // indices into the device counter array (uint64 each)
@@ -40,6 +45,8 @@ enum Counter {
     CNT_NUMERIC, CNT_BORDER, CNT_K6_LOOKUPS,
     CNT_K2A_TRIED, CNT_K2A_CERTIFIED, CNT_K2A_STEPS,  // 13, 14, 15
     CNT_K2A_WORK,                                     // 16: steps x R0 x (1 + k') useful FMAs
+    CNT_K2W_CERTIFIED, CNT_K2W_PIVOTS, CNT_K2W_WORK,  // 17, 18, 19: vertex walk (pivots x basic rows x columns FMAs)
+    CNT_K2W_GIVEUP,                                   // 20: drives abandoned (iteration cap, empty face, dependent row)
     CNT_COUNT = 24
 };
 

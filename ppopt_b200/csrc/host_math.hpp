@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace ppgpu {
@@ -41,6 +42,12 @@ struct ReducedProgram {
     vec th_lo, th_hi;
     // originals (row major), kept for region emission
     vec A, b, F, At_theta, bt, Q, c, H;
+    // K2w: dictionary of ONE feasible vertex of {z : Gf z <= h} in slack form  s_B = beta - D s_N  (wk_nb x wk_ld,
+    // column 0 = beta, column 1 + j = coefficient of the nonbasic slack wk_nvar[j]); wk_ok = 0 when the polyhedron has
+    // no vertex (Gf not of full column rank), is empty, or the host phase 1 did not converge: the walk kernel is then off
+    int wk_ok = 0, wk_nb = 0, wk_ld = 0;
+    vec wk_D0;
+    std::vector<int> wk_bvar, wk_nvar;
     std::string error;
 };
 
@@ -91,6 +98,104 @@ inline void householder_qr_full(vec& M, int r, int c, vec& Qf) {
             for (int i = j; i < r; ++i) Qf[(size_t)rr * r + i] -= d * v[i];
         }
     }
+}
+
+
+// One Gauss-Jordan exchange of a slack dictionary  s_B = beta - D s_N  held as rows [beta | D] (nb x ld): basic row l
+// leaves, nonbasic column j (0-based, stored in column 1 + j) enters.
+inline void dict_pivot(vec& D, int nb, int ld, int l, int j) {
+    const int cj = 1 + j;
+    const double inv = 1.0 / D[(size_t)l * ld + cj];
+    vec q(ld);
+    for (int c = 0; c < ld; ++c) q[c] = D[(size_t)l * ld + c] * inv;
+    q[cj] = inv;
+    for (int r = 0; r < nb; ++r) {
+        if (r == l) continue;
+        const double col = D[(size_t)r * ld + cj];
+        if (col == 0.0) continue;
+        for (int c = 0; c < ld; ++c)
+            if (c != cj) D[(size_t)r * ld + c] -= col * q[c];
+        D[(size_t)r * ld + cj] = -col * inv;
+    }
+    for (int c = 0; c < ld; ++c) D[(size_t)l * ld + c] = q[c];
+}
+
+// K2w set-up: a feasible vertex of F = {z : Gf z <= h} (Gf = T0[:, 1..nfree], h = T0[:, 0]) as a slack dictionary.
+// (1) the free variables z are exchanged against slacks with partial pivoting (the rows that take a z are dropped: z is
+// never needed again), (2) a composite phase 1 (maximise the sum of the negative slacks, Dantzig, Bland after stalling)
+// makes the vertex feasible.  Runs once per program; every feasibility certificate of K2w is a vertex reached from this
+// one by primal simplex pivots (k2w_walk.cu).
+inline void build_walk_dictionary(ReducedProgram& P) {
+    P.wk_ok = 0;
+    const int R0 = P.R0, nf = P.nfree, dc = nf + 2, ld = nf + 1;
+    if (nf < 1 || nf > 64 || R0 <= nf || R0 > 256) return;
+    // start: every slack basic, columns = free z:  s_i = h_i - sum_c Gf[i][c] z_c
+    vec D((size_t)R0 * ld);
+    for (int i = 0; i < R0; ++i) {
+        D[(size_t)i * ld] = P.T0[(size_t)i * dc];
+        for (int c = 0; c < nf; ++c) D[(size_t)i * ld + 1 + c] = P.T0[(size_t)i * dc + 1 + c];
+    }
+    std::vector<int> rowvar(R0), colvar(nf, -1);   // rowvar: slack id, or -1 once the row holds a z
+    for (int i = 0; i < R0; ++i) rowvar[i] = i;
+    for (int c = 0; c < nf; ++c) {
+        int best = -1; double bv = 0.0;
+        for (int i = 0; i < R0; ++i)
+            if (rowvar[i] >= 0 && std::fabs(D[(size_t)i * ld + 1 + c]) > bv) { bv = std::fabs(D[(size_t)i * ld + 1 + c]); best = i; }
+        if (best < 0 || bv < 1e-9) return;   // Gf has no full column rank: F has no vertex
+        dict_pivot(D, R0, ld, best, c);
+        colvar[c] = rowvar[best];
+        rowvar[best] = -1;
+    }
+    const int nb = R0 - nf;
+    vec E((size_t)nb * ld);
+    std::vector<int> bvar(nb);
+    for (int i = 0, o = 0; i < R0; ++i)
+        if (rowvar[i] >= 0) {
+            for (int c = 0; c < ld; ++c) E[(size_t)o * ld + c] = D[(size_t)i * ld + c];
+            bvar[o++] = rowvar[i];
+        }
+    // phase 1
+    int stall = 0;
+    for (int it = 0; it < 200 * (R0 + nf); ++it) {
+        vec g(nf, 0.0);
+        bool any = false;
+        for (int i = 0; i < nb; ++i)
+            if (E[(size_t)i * ld] < -1e-9) {
+                any = true;
+                for (int j = 0; j < nf; ++j) g[j] -= E[(size_t)i * ld + 1 + j];
+            }
+        if (!any) { P.wk_ok = 1; break; }
+        int j = -1;
+        if (stall < 20) {
+            double bg = 1e-9;
+            for (int c = 0; c < nf; ++c) if (g[c] > bg) { bg = g[c]; j = c; }
+        } else {
+            for (int c = 0; c < nf; ++c) if (g[c] > 1e-9 && (j < 0 || colvar[c] < colvar[j])) j = c;
+        }
+        if (j < 0) return;   // no improving direction: F is empty (or numerically so)
+        auto ratio = [&](int i) {
+            const double bi = E[(size_t)i * ld], a = E[(size_t)i * ld + 1 + j];
+            if (bi >= -1e-9) return a > 1e-9 ? (bi > 0.0 ? bi : 0.0) / a : (double)INFINITY;   // a feasible row must stay feasible
+            return a < -1e-9 ? bi / a : (double)INFINITY;                                     // an infeasible row stops at zero
+        };
+        double step = INFINITY;
+        for (int i = 0; i < nb; ++i) step = std::fmin(step, ratio(i));
+        int l = -1; double lp = 0.0;
+        for (int i = 0; i < nb && step < INFINITY; ++i) {
+            if (ratio(i) > step + 1e-12 * (1.0 + step)) continue;
+            const double a = std::fabs(E[(size_t)i * ld + 1 + j]);
+            const bool better = stall < 20 ? a > lp : (l < 0 || bvar[i] < bvar[l]);
+            if (better) { l = i; lp = a; }
+        }
+        if (l < 0) return;
+        stall = step <= 1e-12 ? stall + 1 : 0;
+        dict_pivot(E, nb, ld, l, j);
+        std::swap(bvar[l], colvar[j]);
+    }
+    if (!P.wk_ok) return;
+    for (int i = 0; i < nb; ++i) if (E[(size_t)i * ld] < 0.0) E[(size_t)i * ld] = 0.0;
+    for (size_t k = 0; k < E.size(); ++k) if (!std::isfinite(E[k])) { P.wk_ok = 0; return; }
+    P.wk_nb = nb; P.wk_ld = ld; P.wk_D0 = E; P.wk_bvar = bvar; P.wk_nvar = colvar;
 }
 
 // Builds the reduced program. Inputs are row-major, equalities are rows 0..ne-1 of A/b/F.
@@ -277,6 +382,7 @@ inline bool reduce_program(int n, int t, int m, int q, int ne, int is_qp, const 
             P.use_gram = 1;
         }
     }
+    build_walk_dictionary(P);
     return true;
 }
 

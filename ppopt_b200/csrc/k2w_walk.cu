@@ -1,0 +1,542 @@
+// K2w - feasibility CERTIFICATES shared between the candidates of an enumeration level by walking over VERTICES.
+//
+// Question answered (per candidate active set A): is {z : g_r.z = h_r (r in A), g_r.z <= h_r (all r)} non-empty?
+// (check_feasibility, /root/reference/src/ppopt/mplp_program.py:411-444 -> Solver.solve_lp, solver.py:211-246: one LP per
+// candidate; mpqp_combinatorial.py:75-92 maps it over the level.)
+//
+// Observation: a feasible VERTEX v of F = {z : G z <= h} certifies EVERY candidate whose rows are all active at v - a
+// nondegenerate vertex has nfree active rows, so it answers up to C(nfree, k') candidates of the level at once, while the
+// relaxation of k2a_relax.cu / k2p_prefix.cu pays ~36 steps x R0 x 3 FMAs for each candidate separately (99.9 % of the
+// candidates of the 100x30x6 program are feasible).  The level is in lexicographic order (mpqp_combinatorial.py:60-61),
+// so the candidates that share their first k'-2 rows (the PREFIX) are contiguous; one warp ("walker") owns a chunk of the
+// level and, prefix by prefix, moves a slack dictionary
+//         s_B = beta - D s_N          (s = h - G z >= 0;  nonbasic slacks are 0: their rows are ACTIVE at the vertex)
+// of the whole polyhedron F from vertex to vertex by primal simplex pivots:
+//   drive(r): make row r nonbasic (active) while the rows in the FIXED set stay nonbasic - minimise s_r over the face of
+//             the fixed rows: entering column = largest positive coefficient of row r, Harris ratio test, stop when r
+//             leaves the basis.  Every vertex on the way is primal feasible.
+//   segment (prefix P):  drive the rows of P one by one and fix them; then for every row a with open candidates: drive a,
+//             fix it, and drive every b whose candidate P+{a,b} is still open.
+//   after EVERY pivot the walker marks all open candidates P+{a,b} of the segment with a, b nonbasic: most candidates are
+//             certified in passing (measured in a numpy model of this walk: 0.66 pivots per candidate at level 5).
+// A certificate is therefore an exact statement: "the rows of A are nonbasic at a vertex whose basic slacks are >= -1e-8"
+// (nonbasic slacks are zero by construction; beta carries the rounding of the pivots only: the dictionary is reloaded from
+// the host-built vertex (host_math.hpp::build_walk_dictionary) at every work item and after K2W_RESET pivots).
+// K2w never decides infeasibility and gives up freely (empty face, dependent row, iteration cap): whatever it leaves
+// open goes to the relaxation (K2a) and then to the simplex (K2) exactly as before.
+#include "common.cuh"
+#include "launch.h"
+#include "lp_core.cuh"
+
+#include <cstdlib>
+
+namespace ppgpu {
+
+constexpr int K2W_MAXFIX = 30;      // longest prefix (k' - 2) the walker handles
+constexpr int K2W_DRIVE_CAP = 400;  // pivots per drive before giving up
+constexpr int K2W_RESET = 3000;     // pivots after which the dictionary is reloaded (bounds the accumulated rounding)
+constexpr double K2W_PIV_MIN = 1e-7;   // smallest entering coefficient worth pivoting on
+constexpr double K2W_NEG_OK = 1e-8;    // a vertex certifies only while every basic slack is >= -K2W_NEG_OK
+
+struct K2wCtx {
+    double* D;        // nb x lds   [beta | coefficients], lds odd: rows over lanes are bank-conflict free
+    double* prow;     // lds        scaled pivot row
+    int* bvar;        // nb         row id basic in dictionary row i
+    int* nvar;        // nf         row id nonbasic in column j
+    int* where;       // R0         >= 0: dictionary row, < 0: ~column
+    uint64_t* orig;   // R0 x W4    segment: bit b of row a = candidate P+{a,b} exists in the segment
+    uint64_t* todo;   // R0 x W4    ... and is still open
+    int* rowstart;    // R0         position in the segment of the first candidate with second-last row a
+    uint64_t* nbm;    // W4         bitmask of the nonbasic rows
+    int* fixrow;      // K2W_MAXFIX rows of the prefix currently fixed, in order
+    int nb, nf, ld, lds, R0, W4;
+};
+
+__device__ __forceinline__ int k2w_top_bit(const uint64_t* m, int W, int* second) {
+    int hi1 = -1, hi2 = -1;
+    for (int w = W - 1; w >= 0 && hi2 < 0; --w) {
+        uint64_t x = m[w];
+        while (x && hi2 < 0) {
+            const int t = w * 64 + 63 - __clzll((long long)x);
+            x &= ~(1ull << (t & 63));
+            if (hi1 < 0) hi1 = t; else hi2 = t;
+        }
+    }
+    *second = hi2;
+    return hi1;
+}
+
+// index of the j-th (0-based) set bit of a 4-word mask held in registers
+__device__ __forceinline__ int k2w_nth(const uint64_t (&m)[4], int j) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const int cnt = __popcll(m[w]);
+        if (j < cnt) {
+            uint64_t x = m[w];
+            for (int s = 0; s < j; ++s) x &= x - 1ull;
+            return w * 64 + __ffsll((long long)x) - 1;
+        }
+        j -= cnt;
+    }
+    return -1;
+}
+
+// reload the host-built vertex
+template <int RPL>
+__device__ __forceinline__ void k2w_reload(const DevProgram& P, const K2wCtx& c, int lane) {
+    for (int e = lane; e < c.nb * c.ld; e += 32) {
+        const int r = e / c.ld, k = e - r * c.ld;
+        c.D[(size_t)r * c.lds + k] = __ldg(P.wk_D0 + e);
+    }
+    for (int w = lane; w < c.W4; w += 32) c.nbm[w] = 0ull;
+    __syncwarp();
+    for (int i = lane; i < c.nb; i += 32) { const int v = __ldg(P.wk_bvar + i); c.bvar[i] = v; c.where[v] = i; }
+    for (int j = lane; j < c.nf; j += 32) {
+        const int v = __ldg(P.wk_nvar + j);
+        c.nvar[j] = v; c.where[v] = ~j;
+        atomicOr(reinterpret_cast<unsigned long long*>(c.nbm + (v >> 6)), 1ull << (v & 63));
+    }
+    __syncwarp();
+}
+
+// 1 / x to full double precision without the IEEE division sequence (x is a pivot / ratio denominator: normal, non-zero)
+__device__ __forceinline__ double k2w_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    return r * fma(-x, r, 2.0);
+}
+
+// basic row l leaves, nonbasic column j enters.  Returns false (uniformly) when some basic slack ends below -K2W_NEG_OK.
+template <int RPL>
+__device__ __forceinline__ bool k2w_pivot(const K2wCtx& c, int l, int j, int lane) {
+    const int cj = 1 + j, lds = c.lds, ld = c.ld, nb = c.nb;
+    double* Dl = c.D + (size_t)l * lds;
+    const double inv = k2w_rcp(Dl[cj]);
+    __syncwarp();
+    for (int k = lane; k < ld; k += 32) c.prow[k] = (k == cj) ? 0.0 : Dl[k] * inv;
+    __syncwarp();
+    double colr[RPL];
+    double* Dr[RPL];
+#pragma unroll
+    for (int rr = 0; rr < RPL; ++rr) {
+        const int r = lane + 32 * rr;
+        Dr[rr] = c.D + (size_t)(r < nb ? r : 0) * lds;
+        colr[rr] = (r < nb && r != l) ? Dr[rr][cj] : 0.0;
+    }
+    const double* __restrict__ q = c.prow;
+    // rank-1 update in groups of K2W_G columns: every load of a group is issued before its first FMA (the compiler cannot
+    // hoist a shared-memory load above a store to another row on its own: one exposed LDS latency per element otherwise)
+    constexpr int G = 8;
+    for (int k0 = 0; k0 < ld; k0 += G) {
+        double qk[G], x[RPL][G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) qk[g] = (k0 + g < ld) ? q[k0 + g] : 0.0;
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+            for (int g = 0; g < G; ++g) x[rr][g] = (k0 + g < ld) ? Dr[rr][k0 + g] : 0.0;
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+            for (int g = 0; g < G; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr)
+            if (colr[rr] != 0.0) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    if (k0 + g < ld) Dr[rr][k0 + g] = x[rr][g];
+            }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int rr = 0; rr < RPL; ++rr) {
+        const int r = lane + 32 * rr;
+        if (r < nb && r != l) {
+            if (colr[rr] != 0.0) Dr[rr][cj] = -colr[rr] * inv;
+            ok = ok && Dr[rr][0] >= -K2W_NEG_OK;
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < ld; k += 32) Dl[k] = (k == cj) ? inv : q[k];
+    if (lane == 0) {
+        const int rl = c.bvar[l], rn = c.nvar[j];
+        c.bvar[l] = rn; c.nvar[j] = rl;
+        c.where[rn] = l; c.where[rl] = ~j;
+        c.nbm[rn >> 6] &= ~(1ull << (rn & 63));
+        c.nbm[rl >> 6] |= 1ull << (rl & 63);
+    }
+    ok = __all_sync(PPG_FULL, ok);
+    __syncwarp();
+    return ok;
+}
+
+// certify candidate (a, b) of the segment (the caller has cleared its todo bit)
+__device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int a, int b) {
+    int rank = 0;
+    const int w = b >> 6;
+    for (int w2 = 0; w2 < w; ++w2) rank += __popcll(c.orig[(size_t)a * c.W4 + w2]);
+    rank += __popcll(c.orig[(size_t)a * c.W4 + w] & ((1ull << (b & 63)) - 1ull));
+    const long long idx = seg_base + c.rowstart[a] + rank;
+    status[idx] = status[idx] | PPG_ST_FEAS;
+}
+
+// marks every open candidate of the segment whose last two rows are nonbasic (full scan: after the prefix is fixed)
+__device__ __forceinline__ int k2w_mark_all(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int lane) {
+    int got = 0;
+    for (int a = lane; a < c.R0; a += 32) {
+        if (!((c.nbm[a >> 6] >> (a & 63)) & 1ull)) continue;
+        for (int w = 0; w < c.W4; ++w) {
+            uint64_t bits = c.nbm[w] & c.todo[(size_t)a * c.W4 + w];
+            if (!bits) continue;
+            c.todo[(size_t)a * c.W4 + w] &= ~bits;
+            while (bits) {
+                const int bb = w * 64 + __ffsll((long long)bits) - 1;
+                bits &= bits - 1ull;
+                k2w_certify(c, status, seg_base, a, bb);
+                ++got;
+            }
+        }
+    }
+    return got;
+}
+
+// after a pivot only the pairs with the row r that has just become nonbasic can be new: (r, b) and (a, r)
+__device__ __forceinline__ int k2w_mark_row(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int r, int lane) {
+    int got = 0;
+    const int rw = r >> 6;
+    const uint64_t rbit = 1ull << (r & 63);
+    for (int a = lane; a < c.R0; a += 32) {
+        if (!((c.nbm[a >> 6] >> (a & 63)) & 1ull)) continue;
+        if (a == r) {
+            for (int w = 0; w < c.W4; ++w) {
+                uint64_t bits = c.nbm[w] & c.todo[(size_t)a * c.W4 + w];
+                if (!bits) continue;
+                c.todo[(size_t)a * c.W4 + w] &= ~bits;
+                while (bits) {
+                    const int bb = w * 64 + __ffsll((long long)bits) - 1;
+                    bits &= bits - 1ull;
+                    k2w_certify(c, status, seg_base, a, bb);
+                    ++got;
+                }
+            }
+        } else if (c.todo[(size_t)a * c.W4 + rw] & rbit) {
+            c.todo[(size_t)a * c.W4 + rw] &= ~rbit;
+            k2w_certify(c, status, seg_base, a, r);
+            ++got;
+        }
+    }
+    return got;
+}
+
+// One walker = one warp.  Work item = the candidate groups (prefix, second-last row) that START in a range of `chunk`
+// candidates.
+template <int RPL>
+__global__ void __launch_bounds__(256, 1)
+k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
+                unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int chunk,
+                int walker_bytes, int lds, int W4) {
+    extern __shared__ unsigned char k2w_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K2wCtx c;
+    c.nb = P.wk_nb; c.nf = P.nfree; c.ld = P.wk_ld; c.lds = lds; c.R0 = P.R0; c.W4 = W4;
+    {
+        unsigned char* base = k2w_smem + (size_t)warp * walker_bytes;
+        c.D = reinterpret_cast<double*>(base); base += (size_t)c.nb * lds * 8;
+        c.prow = reinterpret_cast<double*>(base); base += (size_t)lds * 8;
+        c.orig = reinterpret_cast<uint64_t*>(base); base += (size_t)c.R0 * W4 * 8;
+        c.todo = reinterpret_cast<uint64_t*>(base); base += (size_t)c.R0 * W4 * 8;
+        c.nbm = reinterpret_cast<uint64_t*>(base); base += (size_t)W4 * 8;
+        c.bvar = reinterpret_cast<int*>(base); base += (size_t)c.nb * 4;
+        c.nvar = reinterpret_cast<int*>(base); base += (size_t)c.nf * 4;
+        c.where = reinterpret_cast<int*>(base); base += (size_t)c.R0 * 4;
+        c.rowstart = reinterpret_cast<int*>(base); base += (size_t)c.R0 * 4;
+        c.fixrow = reinterpret_cast<int*>(base);
+    }
+    const int W = P.W, R0 = P.R0, nb = c.nb, nf = c.nf;
+    const int p = k_act >= 2 ? k_act - 2 : 0;
+    unsigned long long n_piv = 0, n_give = 0;
+    int n_cert = 0;
+    // prefix words / last two rows of candidate q
+    auto split = [&](long long q, uint64_t (&pf)[4], int& a, int& b) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) pf[w] = w < W ? masks[q * W + w] : 0ull;
+        b = k2w_top_bit(pf, W, &a);
+        if (k_act < 2) a = b;
+        pf[b >> 6] &= ~(1ull << (b & 63));
+        if (k_act >= 2) pf[a >> 6] &= ~(1ull << (a & 63));
+    };
+    // first index in [from, limit) whose prefix (and, with a_ref >= 0, second-last row) differs from pf0 / a_ref; limit if none
+    auto seg_end = [&](long long from, long long limit, const uint64_t (&pf0)[4], int a_ref) -> long long {
+        for (long long q0 = from; q0 < limit; q0 += 32) {
+            const long long q = q0 + lane;
+            bool same = true;
+            if (q < limit) {
+                uint64_t m[4]; int a1, b1;
+                split(q, m, a1, b1);
+                same = m[0] == pf0[0] && m[1] == pf0[1] && m[2] == pf0[2] && m[3] == pf0[3] && (a_ref < 0 || a1 == a_ref);
+            }
+            const unsigned diff = __ballot_sync(PPG_FULL, !same);
+            if (diff) return q0 + __ffs((int)diff) - 1;
+        }
+        return limit;
+    };
+    for (;;) {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(queue, (unsigned long long)chunk);
+        const long long c0 = (long long)__shfl_sync(PPG_FULL, v, 0);
+        if (c0 >= n) break;
+        const long long c1 = (c0 + chunk < n) ? c0 + chunk : n;
+        // a walker owns the GROUPS (prefix, second-last row) that start in [c0, c1): a group is never split, so that the
+        // certificates of one vertex reach all its candidates, while the long segments of the first prefixes (thousands
+        // of candidates with one prefix) still spread over many walkers
+        long long i = c0, own_end = c1;
+        if (c0 > 0) {
+            uint64_t pfp[4]; int a_, b_;
+            split(c0 - 1, pfp, a_, b_);
+            i = seg_end(c0, n, pfp, k_act >= 2 ? a_ : -1);
+        }
+        if (i >= c1) continue;
+        if (c1 < n) {
+            uint64_t pfp[4]; int a_, b_;
+            split(c1 - 1, pfp, a_, b_);
+            own_end = seg_end(c1, n, pfp, k_act >= 2 ? a_ : -1);
+        }
+        k2w_reload<RPL>(P, c, lane);
+        int npiv = 0, nfixed = 0;
+        bool vertex_ok = true;
+        while (i < own_end) {
+            // ---- segment [i, s1): candidates with the prefix of candidate i (inside what this walker owns)
+            uint64_t pf0[4];
+            int a0, b0;
+            split(i, pf0, a0, b0);
+            const long long s1 = seg_end(i + 1, own_end, pf0, -1);
+            // ---- bitmaps of the segment
+            for (int e = lane; e < R0 * W4; e += 32) { c.orig[e] = 0ull; c.todo[e] = 0ull; }
+            __syncwarp();
+            int any = 0;
+            for (long long q0 = i; q0 < s1; q0 += 32) {
+                const long long q = q0 + lane;
+                int a1 = -1, b1 = -1;
+                bool open = false;
+                if (q < s1) {
+                    uint64_t m[4];
+                    split(q, m, a1, b1);
+                    const uint8_t sb = status[q];
+                    open = (sb & PPG_ST_RANK) && !(sb & PPG_ST_FEAS);
+                    atomicOr(reinterpret_cast<unsigned long long*>(c.orig + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
+                    if (open) atomicOr(reinterpret_cast<unsigned long long*>(c.todo + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
+                }
+                int aprev = __shfl_up_sync(PPG_FULL, a1, 1);
+                if (lane == 0) {
+                    aprev = -1;
+                    if (q0 > i) { uint64_t m[4]; int b2; split(q0 - 1, m, aprev, b2); }
+                }
+                if (q < s1 && a1 != aprev) c.rowstart[a1] = (int)(q - i);
+                any |= __any_sync(PPG_FULL, open) ? 1 : 0;
+            }
+            __syncwarp();
+            if (!any) { i = s1; continue; }
+            // ---- the walk of this segment: ONE drive loop fed by a small state machine
+            //   stage 0: fix prefix row f        (no marking: the prefix is not in place yet)
+            //   stage 1: make row a nonbasic     (marking on)
+            //   stage 2: make row b nonbasic     (marking on, a fixed as well)
+            int stage = 0, f = 0, a = -1, t = -1;
+            uint64_t pmask = 0ull, fm = 0ull;
+            bool restart = (npiv > K2W_RESET) || !vertex_ok;
+            for (;;) {
+                if (restart) {
+                    k2w_reload<RPL>(P, c, lane);
+                    n_piv += npiv; npiv = 0; nfixed = 0; vertex_ok = true; restart = false;
+                    stage = 0; f = 0; a = -1;
+                }
+                // -- next target
+                if (stage == 0) {
+                    if (f == 0) {
+                        // keep the common head of what is fixed already
+                        int keep = 0;
+                        for (; keep < nfixed && keep < p; ++keep)
+                            if (c.fixrow[keep] != k2w_nth(pf0, keep)) break;
+                        nfixed = keep; f = keep;
+                        pmask = 0ull;
+                        for (int g = 0; g < nfixed; ++g) pmask |= 1ull << (~c.where[c.fixrow[g]]);
+                    }
+                    if (f < p) {
+                        t = k2w_nth(pf0, f); fm = pmask;
+                    } else {
+                        n_cert += k2w_mark_all(c, status, i, lane);
+                        __syncwarp();
+                        stage = 1; a = -1;
+                    }
+                }
+                if (stage == 1) {
+                    int na = -1;
+                    for (int x = a + 1; x < R0 && na < 0; ++x)
+                        for (int w = 0; w < W4; ++w)
+                            if (c.todo[(size_t)x * W4 + w]) { na = x; break; }
+                    if (na < 0) break;   // segment done
+                    a = na; t = a; fm = pmask;
+                    if (npiv > K2W_RESET) { restart = true; continue; }   // long segment: fresh dictionary, same prefix
+                }
+                if (stage == 2) {
+                    int b = -1;
+                    for (int w = 0; w < W4 && b < 0; ++w) {
+                        const uint64_t x = c.todo[(size_t)a * W4 + w];
+                        if (x) b = w * 64 + __ffsll((long long)x) - 1;
+                    }
+                    if (b < 0) { stage = 1; continue; }
+                    t = b;
+                }
+                // -- drive row t into the nonbasic set while the columns in fm stay put
+                bool reached = false;
+                for (int it = 0; it < K2W_DRIVE_CAP; ++it) {
+                    const int wi = c.where[t];
+                    if (wi < 0) { reached = true; break; }
+                    const double* Di = c.D + (size_t)wi * lds;
+                    const double bi = Di[0];
+                    // entering column: largest positive coefficient of the target row among the free columns (degenerate
+                    // target: largest magnitude - a step of length zero is feasible in either direction)
+                    const bool degen = bi <= 1e-11;
+                    double best = 0.0; int bj = 0x7fffffff;
+                    for (int j = lane; j < nf; j += 32) {
+                        if ((fm >> j) & 1ull) continue;
+                        double x = Di[1 + j];
+                        if (degen) x = fabs(x);
+                        if (x > best) { best = x; bj = j; }
+                    }
+                    const double wbest = warp_max_nonneg(best);
+                    if (!(wbest > K2W_PIV_MIN)) break;   // s_t cannot decrease on this face (empty face / dependent row)
+                    const int j = __reduce_min_sync(PPG_FULL, best == wbest ? bj : 0x7fffffff);
+                    int l = wi;
+                    if (!degen) {
+                        // Harris ratio test over the basic rows (lanes over rows); the target row wins when it is eligible
+                        double col[RPL], rat[RPL];
+                        double hb = CUDART_INF, trat = CUDART_INF;
+#pragma unroll
+                        for (int rr = 0; rr < RPL; ++rr) {
+                            const int r = lane + 32 * rr;
+                            col[rr] = 0.0; rat[rr] = CUDART_INF;
+                            if (r < nb) {
+                                const double av = c.D[(size_t)r * lds + 1 + j];
+                                if (av > PPG_TINY) {
+                                    const double bv = fmax(c.D[(size_t)r * lds], 0.0);
+                                    const double ia = k2w_rcp(av);
+                                    col[rr] = av; rat[rr] = bv * ia;
+                                    hb = fmin(hb, (bv + PPG_HARRIS) * ia);
+                                    if (r == wi) trat = rat[rr];
+                                }
+                            }
+                        }
+                        hb = warp_min_nonneg(hb);
+                        trat = __shfl_sync(PPG_FULL, trat, wi & 31);
+                        if (!(trat <= hb)) {
+                            double lp = 0.0; int lrow = 0x7fffffff;
+#pragma unroll
+                            for (int rr = 0; rr < RPL; ++rr)
+                                if (rat[rr] <= hb && col[rr] > lp) { lp = col[rr]; lrow = lane + 32 * rr; }
+                            const double wp = warp_max_nonneg(lp);
+                            l = __reduce_min_sync(PPG_FULL, (lrow != 0x7fffffff && lp == wp) ? lrow : 0x7fffffff);
+                            if (l == 0x7fffffff) break;   // (cannot happen: the target row itself blocks)
+                        }
+                    }
+                    const int rl = c.bvar[l];
+                    vertex_ok = k2w_pivot<RPL>(c, l, j, lane);
+                    ++npiv;
+                    if (!vertex_ok) break;
+                    if (stage != 0) n_cert += k2w_mark_row(c, status, i, rl, lane);
+                    __syncwarp();
+                }
+                if (!vertex_ok) {
+                    // a basic slack fell below the certification band: nothing is marked from such a dictionary; start over
+                    // from the host vertex (this segment's open candidates stay open for the relaxation)
+                    ++n_give;
+                    break;
+                }
+                // -- what the drive means for the walk
+                if (stage == 0) {
+                    if (!reached) { ++n_give; break; }   // prefix not reachable here: the segment is left to the relaxation
+                    if (lane == 0) c.fixrow[f] = t;
+                    __syncwarp();
+                    pmask |= 1ull << (~c.where[t]);
+                    nfixed = ++f;
+                } else if (stage == 1) {
+                    if (!reached) {
+                        ++n_give;
+                        // nothing with this a can be certified by the walk
+                        if (lane == 0) for (int w = 0; w < W4; ++w) c.todo[(size_t)a * W4 + w] = 0ull;
+                        __syncwarp();
+                    } else if (k_act >= 2) {
+                        fm = pmask | (1ull << (~c.where[a]));
+                        stage = 2;
+                    }
+                    // (single-row candidates were marked by the drive itself)
+                } else {
+                    // certified by the marking or not: this candidate is not tried again
+                    if (lane == 0) c.todo[(size_t)a * W4 + (t >> 6)] &= ~(1ull << (t & 63));
+                    __syncwarp();
+                    if (!reached) ++n_give;
+                }
+            }
+            i = s1;
+        }
+        n_piv += npiv;
+    }
+    n_cert = __reduce_add_sync(PPG_FULL, n_cert);
+    if (lane == 0 && (n_piv || n_cert)) {
+        atomicAdd(&counters[CNT_K2W_CERTIFIED], (unsigned long long)n_cert);
+        atomicAdd(&counters[CNT_K2W_PIVOTS], n_piv);
+        atomicAdd(&counters[CNT_K2W_WORK], n_piv * (unsigned long long)(c.nb * c.ld));
+        atomicAdd(&counters[CNT_K2W_GIVEUP], n_give);
+    }
+}
+
+template <int RPL>
+static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                                unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st,
+                                bool* handled) {
+    const int nb = P.wk_nb, ld = P.wk_ld, lds = ld | 1, W4 = (P.R0 + 63) / 64;
+    size_t wb = (size_t)nb * lds * 8 + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
+                (size_t)(nb + P.nfree + 2 * P.R0 + K2W_MAXFIX + 2) * 4;
+    wb = (wb + 15) & ~(size_t)15;
+    int wpc = (int)((size_t)(226 * 1024) / wb);
+    if (wpc > 8) wpc = 8;
+    if (wpc < 1) return cudaSuccess;   // dictionary too large for shared memory: the relaxation handles the level
+    auto kern = k2w_walk_kernel<RPL>;
+    const size_t smem = wb * wpc;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long walkers = (long long)sm_count * wpc;
+    long long chunk = n / (walkers * 8);
+    if (chunk > 4096) chunk = 4096;
+    if (chunk < 128) chunk = 128;
+    long long grid = (n + chunk * wpc - 1) / (chunk * wpc);
+    if (grid > sm_count) grid = sm_count;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 32 * wpc, smem, st>>>(P, masks, n, k_act, status, queue, counters, (int)chunk, (int)wb, lds, W4);
+    *handled = true;
+    return cudaGetLastError();
+}
+
+// *handled == false: the walk is off for this program / level (no vertex dictionary, level too small, prefix too long)
+cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled) {
+    *handled = false;
+    static const int on = getenv("PPGPU_K2W") ? atoi(getenv("PPGPU_K2W")) : 1;
+    if (!on || !P.wk_ok || k_act < 1 || k_act - 2 > K2W_MAXFIX || P.W > 4 || P.nfree > 64) return cudaSuccess;
+    const int rpl = (P.wk_nb + 31) / 32;
+#define K2W_GO(R) return launch_k2w_t<R>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled)
+    switch (rpl) {
+        case 1: K2W_GO(1);
+        case 2: K2W_GO(2);
+        case 3: K2W_GO(3);
+        case 4: K2W_GO(4);
+        case 5: K2W_GO(5);
+        case 6: K2W_GO(6);
+        case 7: K2W_GO(7);
+        case 8: K2W_GO(8);
+        default: return cudaSuccess;
+    }
+#undef K2W_GO
+}
+
+}  // namespace ppgpu

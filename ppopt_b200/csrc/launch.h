@@ -18,6 +18,9 @@ cudaError_t launch_k2a(const DevProgram& P, const uint64_t* masks, long long n, 
 cudaError_t launch_k2a_prefix(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                               unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count,
                               cudaStream_t st, bool* handled);
+// K2w: feasibility certificates shared between the candidates of a prefix by a primal-simplex walk over vertices
+cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled);
 cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st);
 // general (LU) path: marks every feasible candidate that the reference would hand to check_optimality

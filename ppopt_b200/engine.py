@@ -70,6 +70,7 @@ class Engine:
         self.W, self.mi, self.R0 = info.words, info.n_ineq, info.region_rows
         self.use_gram, self.max_depth, self.sm_count = bool(info.use_gram), info.max_depth, info.sm_count
         self.lp_columns = info.lp_columns
+        self.has_walk_vertex = bool(info.reserved)
         self.h2d_bytes = sum(v.nbytes for v in a.values() if isinstance(v, numpy.ndarray))
         self.d2h_bytes = 0
 
@@ -85,6 +86,9 @@ class Engine:
             pass
 
     # ---- thin wrappers -------------------------------------------------------------------------------------------
+    def set_option(self, option: int, value: int):
+        _lib.check(self.lib.ppgpu_set_option(self.h, int(option), int(value)), 'set_option')
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
 

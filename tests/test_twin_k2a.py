@@ -79,3 +79,23 @@ def test_certification_rate_on_the_headline_program(prefix):
         else:
             assert (flags[ok] == 1).sum() >= 0.97 * ((st & 2) != 0)[ok].sum()
         assert 5 < steps[ok].mean() < 45
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_walk_start_vertex_is_a_feasible_vertex(name):
+    """host_math.hpp::build_walk_dictionary (the start of every K2w walk): the nonbasic rows form a nonsingular system, the
+    dictionary equals the one numpy derives from that basis, and the vertex is primal feasible"""
+    from twin_binding import Twin
+    tw = Twin.from_npz(os.path.join(GOLDEN, name + '.npz'))
+    wd = tw.walk_dict()
+    if wd is None:
+        pytest.skip('feasibility polyhedron without a vertex: the walk is off for this program')
+    D0, bvar, nvar, T0 = wd
+    h, G = T0[:, 0], T0[:, 1:-1]
+    assert sorted(bvar.tolist() + nvar.tolist()) == list(range(G.shape[0]))
+    M = G @ numpy.linalg.inv(G[nvar])
+    beta = (h - M @ h[nvar])[bvar]
+    scale = max(1.0, float(numpy.max(numpy.abs(h))))
+    assert numpy.max(numpy.abs(D0[:, 1:] + M[bvar])) <= 1e-9 * max(1.0, float(numpy.max(numpy.abs(M))))
+    assert numpy.max(numpy.abs(D0[:, 0] - numpy.maximum(beta, 0.0))) <= 1e-9 * scale
+    assert beta.min() >= -1e-9 * scale
