@@ -177,7 +177,7 @@ int ppgpu_root_level(ppgpu_program* p, uint64_t* d_masks, int64_t* h_count, ppgp
 // candidates of one ppgpu_level_eval call are processed in chunks of this many, so that the K2a -> K2 hand-over buffers
 // (one residual vector per uncertified candidate) stay bounded however large the level is
 static long long level_chunk() {
-    static const long long c = getenv("PPGPU_CHUNK") ? atoll(getenv("PPGPU_CHUNK")) : (1ll << 22);
+    static const long long c = getenv("PPGPU_CHUNK") ? atoll(getenv("PPGPU_CHUNK")) : (1ll << 24);
     return c < 1024 ? 1024 : c;
 }
 

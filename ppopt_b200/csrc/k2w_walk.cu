@@ -81,13 +81,24 @@ __device__ __forceinline__ int k2w_nth(const uint64_t (&m)[4], int j) {
     return -1;
 }
 
-// reload the host-built vertex
-template <int RPL>
-__device__ __forceinline__ void k2w_reload(const DevProgram& P, const K2wCtx& c, int lane) {
-    for (int e = lane; e < c.nb * c.ld; e += 32) {
-        const int r = e / c.ld, k = e - r * c.ld;
-        c.D[(size_t)r * c.lds + k] = __ldg(P.wk_D0 + e);
-    }
+// 1 / x to full double precision without the IEEE division sequence (x is a pivot / ratio denominator: normal, non-zero)
+__device__ __forceinline__ double k2w_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    return r * fma(-x, r, 2.0);
+}
+
+// labels of a Gauss-Jordan exchange (basic row l <-> nonbasic column j); lane 0
+__device__ __forceinline__ void k2w_swap_labels(const K2wCtx& c, int l, int j) {
+    const int rl = c.bvar[l], rn = c.nvar[j];
+    c.bvar[l] = rn; c.nvar[j] = rl;
+    c.where[rn] = l; c.where[rl] = ~j;
+    c.nbm[rn >> 6] &= ~(1ull << (rn & 63));
+    c.nbm[rl >> 6] |= 1ull << (rl & 63);
+}
+
+__device__ __forceinline__ void k2w_reload_labels(const DevProgram& P, const K2wCtx& c, int lane) {
     for (int w = lane; w < c.W4; w += 32) c.nbm[w] = 0ull;
     __syncwarp();
     for (int i = lane; i < c.nb; i += 32) { const int v = __ldg(P.wk_bvar + i); c.bvar[i] = v; c.where[v] = i; }
@@ -99,77 +110,202 @@ __device__ __forceinline__ void k2w_reload(const DevProgram& P, const K2wCtx& c,
     __syncwarp();
 }
 
-// 1 / x to full double precision without the IEEE division sequence (x is a pivot / ratio denominator: normal, non-zero)
-__device__ __forceinline__ double k2w_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = r * fma(-x, r, 2.0);
-    return r * fma(-x, r, 2.0);
-}
-
-// basic row l leaves, nonbasic column j enters.  Returns false (uniformly) when some basic slack ends below -K2W_NEG_OK.
-template <int RPL>
-__device__ __forceinline__ bool k2w_pivot(const K2wCtx& c, int l, int j, int lane) {
-    const int cj = 1 + j, lds = c.lds, ld = c.ld, nb = c.nb;
-    double* Dl = c.D + (size_t)l * lds;
-    const double inv = k2w_rcp(Dl[cj]);
-    __syncwarp();
-    for (int k = lane; k < ld; k += 32) c.prow[k] = (k == cj) ? 0.0 : Dl[k] * inv;
-    __syncwarp();
-    double colr[RPL];
-    double* Dr[RPL];
-#pragma unroll
-    for (int rr = 0; rr < RPL; ++rr) {
-        const int r = lane + 32 * rr;
-        Dr[rr] = c.D + (size_t)(r < nb ? r : 0) * lds;
-        colr[rr] = (r < nb && r != l) ? Dr[rr][cj] : 0.0;
+// ---- storage policy A: the dictionary in SHARED memory (any size that fits), lanes over rows
+template <int RPL_>
+struct K2wSmemDict {
+    static constexpr int RPL = RPL_;
+    static constexpr bool IN_SMEM = true;
+    __device__ __forceinline__ void reload(const DevProgram& P, const K2wCtx& c, int lane) {
+        for (int e = lane; e < c.nb * c.ld; e += 32) {
+            const int r = e / c.ld, k = e - r * c.ld;
+            c.D[(size_t)r * c.lds + k] = __ldg(P.wk_D0 + e);
+        }
+        k2w_reload_labels(P, c, lane);
     }
-    const double* __restrict__ q = c.prow;
-    // rank-1 update in groups of K2W_G columns: every load of a group is issued before its first FMA (the compiler cannot
-    // hoist a shared-memory load above a store to another row on its own: one exposed LDS latency per element otherwise)
-    constexpr int G = 8;
-    for (int k0 = 0; k0 < ld; k0 += G) {
-        double qk[G], x[RPL][G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) qk[g] = (k0 + g < ld) ? q[k0 + g] : 0.0;
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr)
-#pragma unroll
-            for (int g = 0; g < G; ++g) x[rr][g] = (k0 + g < ld) ? Dr[rr][k0 + g] : 0.0;
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr)
-#pragma unroll
-            for (int g = 0; g < G; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
-#pragma unroll
-        for (int rr = 0; rr < RPL; ++rr)
-            if (colr[rr] != 0.0) {
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                    if (k0 + g < ld) Dr[rr][k0 + g] = x[rr][g];
-            }
+    // right-hand side of basic row wi and its largest eligible coefficient (uniform results)
+    __device__ __forceinline__ void target_scan(const K2wCtx& c, int wi, uint64_t fm, int lane, double& bi, double& wbest, int& j) {
+        const double* Di = c.D + (size_t)wi * c.lds;
+        bi = Di[0];
+        const bool degen = bi <= 1e-11;
+        double best = 0.0; int bj = 0x7fffffff;
+        for (int jj = lane; jj < c.nf; jj += 32) {
+            if ((fm >> jj) & 1ull) continue;
+            double x = Di[1 + jj];
+            if (degen) x = fabs(x);
+            if (x > best) { best = x; bj = jj; }
+        }
+        wbest = warp_max_nonneg(best);
+        j = __reduce_min_sync(PPG_FULL, best == wbest ? bj : 0x7fffffff);
     }
-    bool ok = true;
+    __device__ __forceinline__ void column(const K2wCtx& c, int j, int lane, double (&col)[RPL], double (&beta)[RPL]) {
 #pragma unroll
-    for (int rr = 0; rr < RPL; ++rr) {
-        const int r = lane + 32 * rr;
-        if (r < nb && r != l) {
-            if (colr[rr] != 0.0) Dr[rr][cj] = -colr[rr] * inv;
-            ok = ok && Dr[rr][0] >= -K2W_NEG_OK;
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int r = lane + 32 * rr;
+            col[rr] = r < c.nb ? c.D[(size_t)r * c.lds + 1 + j] : 0.0;
+            beta[rr] = r < c.nb ? c.D[(size_t)r * c.lds] : 0.0;
         }
     }
-    __syncwarp();
-    for (int k = lane; k < ld; k += 32) Dl[k] = (k == cj) ? inv : q[k];
-    if (lane == 0) {
-        const int rl = c.bvar[l], rn = c.nvar[j];
-        c.bvar[l] = rn; c.nvar[j] = rl;
-        c.where[rn] = l; c.where[rl] = ~j;
-        c.nbm[rn >> 6] &= ~(1ull << (rn & 63));
-        c.nbm[rl >> 6] |= 1ull << (rl & 63);
+    // basic row l leaves, nonbasic column j enters.  Returns false (uniformly) when some basic slack ends below -K2W_NEG_OK.
+    __device__ __forceinline__ bool pivot(const K2wCtx& c, int l, int j, int lane) {
+        const int cj = 1 + j, lds = c.lds, ld = c.ld, nb = c.nb;
+        double* Dl = c.D + (size_t)l * lds;
+        const double inv = k2w_rcp(Dl[cj]);
+        __syncwarp();
+        for (int k = lane; k < ld; k += 32) c.prow[k] = (k == cj) ? 0.0 : Dl[k] * inv;
+        __syncwarp();
+        double colr[RPL];
+        double* Dr[RPL];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int r = lane + 32 * rr;
+            Dr[rr] = c.D + (size_t)(r < nb ? r : 0) * lds;
+            colr[rr] = (r < nb && r != l) ? Dr[rr][cj] : 0.0;
+        }
+        const double* __restrict__ q = c.prow;
+        // rank-1 update in groups of G columns: every load of a group is issued before its first FMA (the compiler cannot
+        // hoist a shared-memory load above a store to another row on its own: one exposed LDS latency per element otherwise)
+        constexpr int G = 8;
+        for (int k0 = 0; k0 < ld; k0 += G) {
+            double qk[G], x[RPL][G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) qk[g] = (k0 + g < ld) ? q[k0 + g] : 0.0;
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+                for (int g = 0; g < G; ++g) x[rr][g] = (k0 + g < ld) ? Dr[rr][k0 + g] : 0.0;
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+                for (int g = 0; g < G; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
+#pragma unroll
+            for (int rr = 0; rr < RPL; ++rr)
+                if (colr[rr] != 0.0) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        if (k0 + g < ld) Dr[rr][k0 + g] = x[rr][g];
+                }
+        }
+        bool ok = true;
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int r = lane + 32 * rr;
+            if (r < nb && r != l) {
+                if (colr[rr] != 0.0) Dr[rr][cj] = -colr[rr] * inv;
+                ok = ok && Dr[rr][0] >= -K2W_NEG_OK;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < ld; k += 32) Dl[k] = (k == cj) ? inv : q[k];
+        if (lane == 0) k2w_swap_labels(c, l, j);
+        ok = __all_sync(PPG_FULL, ok);
+        __syncwarp();
+        return ok;
     }
-    ok = __all_sync(PPG_FULL, ok);
-    __syncwarp();
-    return ok;
-}
+};
+
+// ---- storage policy B: the dictionary in REGISTERS - lane (r & 31) holds basic row r in slot r >> 5, DC = columns incl.
+// the right-hand side (exactly wk_ld).  Only the scaled pivot row crosses shared memory (DC doubles per pivot); the rank-1
+// update is RPL x DC back-to-back DFMAs on registers.  Register arrays are only ever indexed by compile-time constants
+// (static_for / reg_pick / reg_set of lp_core.cuh), else the dictionary would fall into local memory.
+template <int RPL_, int DC>
+struct K2wRegDict {
+    static constexpr int RPL = RPL_;
+    static constexpr bool IN_SMEM = false;
+    double T[RPL][DC];
+    __device__ __forceinline__ void reload(const DevProgram& P, const K2wCtx& c, int lane) {
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            const int r = lane + 32 * rr;
+#pragma unroll
+            for (int k = 0; k < DC; ++k) T[rr][k] = r < c.nb ? __ldg(P.wk_D0 + (size_t)r * DC + k) : 0.0;
+        });
+        k2w_reload_labels(P, c, lane);
+    }
+    __device__ __forceinline__ void target_scan(const K2wCtx& c, int wi, uint64_t fm, int lane, double& bi, double& wbest, int& j) {
+        // the owner lane scans its own row (no shared-memory round trip), the result is broadcast
+        const int slot = wi >> 5, owner = wi & 31;
+        double b0 = 0.0, best = 0.0; int bj = 0x7fffffff;
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            if (rr == slot) {
+                b0 = T[rr][0];
+                const bool degen = b0 <= 1e-11;
+#pragma unroll
+                for (int k = 1; k < DC; ++k) {
+                    double x = T[rr][k];
+                    if (degen) x = fabs(x);
+                    if (!((fm >> (k - 1)) & 1ull) && x > best) { best = x; bj = k - 1; }
+                }
+            }
+        });
+        bi = shfl_d(b0, owner);
+        wbest = shfl_d(best, owner);
+        j = __shfl_sync(PPG_FULL, bj, owner);
+    }
+    __device__ __forceinline__ void column(const K2wCtx& c, int j, int lane, double (&col)[RPL], double (&beta)[RPL]) {
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            col[rr] = (lane + 32 * rr < c.nb) ? reg_pick<DC>(T[rr], 1 + j) : 0.0;
+            beta[rr] = T[rr][0];
+        });
+    }
+    __device__ __forceinline__ bool pivot(const K2wCtx& c, int l, int j, int lane) {
+        const int cj = 1 + j, slot = l >> 5, owner = l & 31, nb = c.nb;
+        double colr[RPL];
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            colr[rr] = reg_pick<DC>(T[rr], cj);
+        });
+        double piv = 0.0;
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            if (rr == slot) piv = colr[rr];
+        });
+        const double inv = k2w_rcp(shfl_d(piv, owner));
+        __syncwarp();
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            if (rr == slot && lane == owner) {
+#pragma unroll
+                for (int k = 0; k < DC; ++k) c.prow[k] = T[rr][k] * inv;
+                c.prow[cj] = 0.0;
+            }
+        });
+        __syncwarp();
+        const double* __restrict__ q = c.prow;
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            const int r = lane + 32 * rr;
+            if (r >= nb || r == l) colr[rr] = 0.0;
+        });
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+            const double qk = q[k];
+            static_for<RPL>([&](auto RR) {
+                constexpr int rr = decltype(RR)::value;
+                T[rr][k] = fma(-colr[rr], qk, T[rr][k]);
+            });
+        }
+        static_for<RPL>([&](auto RR) {
+            constexpr int rr = decltype(RR)::value;
+            const int r = lane + 32 * rr;
+            if (r == l) {
+                // the pivot row itself: the scaled row, 1 / pivot in the exchanged column
+#pragma unroll
+                for (int k = 0; k < DC; ++k) T[rr][k] = q[k];
+                reg_set<DC>(T[rr], cj, inv);
+            } else {
+                reg_set<DC>(T[rr], cj, -colr[rr] * inv);   // (rows beyond nb and zero entries: stays 0)
+                ok = ok && (r >= nb || T[rr][0] >= -K2W_NEG_OK);
+            }
+        });
+        if (lane == 0) k2w_swap_labels(c, l, j);
+        ok = __all_sync(PPG_FULL, ok);
+        __syncwarp();
+        return ok;
+    }
+};
 
 // certify candidate (a, b) of the segment (the caller has cleared its todo bit)
 __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int a, int b) {
@@ -231,18 +367,20 @@ __device__ __forceinline__ int k2w_mark_row(const K2wCtx& c, uint8_t* __restrict
 
 // One walker = one warp.  Work item = the candidate groups (prefix, second-last row) that START in a range of `chunk`
 // candidates.
-template <int RPL>
+template <class Dict>
 __global__ void __launch_bounds__(256, 1)
 k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int chunk,
                 int walker_bytes, int lds, int W4) {
     extern __shared__ unsigned char k2w_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int RPL = Dict::RPL;
+    Dict dict;
     K2wCtx c;
     c.nb = P.wk_nb; c.nf = P.nfree; c.ld = P.wk_ld; c.lds = lds; c.R0 = P.R0; c.W4 = W4;
     {
         unsigned char* base = k2w_smem + (size_t)warp * walker_bytes;
-        c.D = reinterpret_cast<double*>(base); base += (size_t)c.nb * lds * 8;
+        c.D = reinterpret_cast<double*>(base); if (Dict::IN_SMEM) base += (size_t)c.nb * lds * 8;
         c.prow = reinterpret_cast<double*>(base); base += (size_t)lds * 8;
         c.orig = reinterpret_cast<uint64_t*>(base); base += (size_t)c.R0 * W4 * 8;
         c.todo = reinterpret_cast<uint64_t*>(base); base += (size_t)c.R0 * W4 * 8;
@@ -302,7 +440,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
             split(c1 - 1, pfp, a_, b_);
             own_end = seg_end(c1, n, pfp, k_act >= 2 ? a_ : -1);
         }
-        k2w_reload<RPL>(P, c, lane);
+        dict.reload(P, c, lane);
         int npiv = 0, nfixed = 0;
         bool vertex_ok = true;
         while (i < own_end) {
@@ -346,7 +484,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
             bool restart = (npiv > K2W_RESET) || !vertex_ok;
             for (;;) {
                 if (restart) {
-                    k2w_reload<RPL>(P, c, lane);
+                    dict.reload(P, c, lane);
                     n_piv += npiv; npiv = 0; nfixed = 0; vertex_ok = true; restart = false;
                     stage = 0; f = 0; a = -1;
                 }
@@ -392,39 +530,29 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                 for (int it = 0; it < K2W_DRIVE_CAP; ++it) {
                     const int wi = c.where[t];
                     if (wi < 0) { reached = true; break; }
-                    const double* Di = c.D + (size_t)wi * lds;
-                    const double bi = Di[0];
                     // entering column: largest positive coefficient of the target row among the free columns (degenerate
                     // target: largest magnitude - a step of length zero is feasible in either direction)
+                    double bi, wbest; int j;
+                    dict.target_scan(c, wi, fm, lane, bi, wbest, j);
                     const bool degen = bi <= 1e-11;
-                    double best = 0.0; int bj = 0x7fffffff;
-                    for (int j = lane; j < nf; j += 32) {
-                        if ((fm >> j) & 1ull) continue;
-                        double x = Di[1 + j];
-                        if (degen) x = fabs(x);
-                        if (x > best) { best = x; bj = j; }
-                    }
-                    const double wbest = warp_max_nonneg(best);
                     if (!(wbest > K2W_PIV_MIN)) break;   // s_t cannot decrease on this face (empty face / dependent row)
-                    const int j = __reduce_min_sync(PPG_FULL, best == wbest ? bj : 0x7fffffff);
                     int l = wi;
                     if (!degen) {
                         // Harris ratio test over the basic rows (lanes over rows); the target row wins when it is eligible
-                        double col[RPL], rat[RPL];
+                        double col[RPL], rat[RPL], beta[RPL];
                         double hb = CUDART_INF, trat = CUDART_INF;
+                        dict.column(c, j, lane, col, beta);
 #pragma unroll
                         for (int rr = 0; rr < RPL; ++rr) {
                             const int r = lane + 32 * rr;
+                            const double av = col[rr];
                             col[rr] = 0.0; rat[rr] = CUDART_INF;
-                            if (r < nb) {
-                                const double av = c.D[(size_t)r * lds + 1 + j];
-                                if (av > PPG_TINY) {
-                                    const double bv = fmax(c.D[(size_t)r * lds], 0.0);
-                                    const double ia = k2w_rcp(av);
-                                    col[rr] = av; rat[rr] = bv * ia;
-                                    hb = fmin(hb, (bv + PPG_HARRIS) * ia);
-                                    if (r == wi) trat = rat[rr];
-                                }
+                            if (r < nb && av > PPG_TINY) {
+                                const double bv = fmax(beta[rr], 0.0);
+                                const double ia = k2w_rcp(av);
+                                col[rr] = av; rat[rr] = bv * ia;
+                                hb = fmin(hb, (bv + PPG_HARRIS) * ia);
+                                if (r == wi) trat = rat[rr];
                             }
                         }
                         hb = warp_min_nonneg(hb);
@@ -440,7 +568,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                         }
                     }
                     const int rl = c.bvar[l];
-                    vertex_ok = k2w_pivot<RPL>(c, l, j, lane);
+                    vertex_ok = dict.pivot(c, l, j, lane);
                     ++npiv;
                     if (!vertex_ok) break;
                     if (stage != 0) n_cert += k2w_mark_row(c, status, i, rl, lane);
@@ -490,24 +618,33 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
     }
 }
 
-template <int RPL>
+#define K2W_COMMA ,
+template <class Dict>
 static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                                 unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st,
                                 bool* handled) {
     const int nb = P.wk_nb, ld = P.wk_ld, lds = ld | 1, W4 = (P.R0 + 63) / 64;
-    size_t wb = (size_t)nb * lds * 8 + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
+    size_t wb = (Dict::IN_SMEM ? (size_t)nb * lds * 8 : 0) + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
                 (size_t)(nb + P.nfree + 2 * P.R0 + K2W_MAXFIX + 2) * 4;
     wb = (wb + 15) & ~(size_t)15;
+    auto kern = k2w_walk_kernel<Dict>;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
     int wpc = (int)((size_t)(226 * 1024) / wb);
+    const int by_regs = 65536 / (32 * (fa.numRegs > 0 ? fa.numRegs : 255));   // warps the register file holds
+    if (wpc > by_regs) wpc = by_regs;
     if (wpc > 8) wpc = 8;
     if (wpc < 1) return cudaSuccess;   // dictionary too large for shared memory: the relaxation handles the level
-    auto kern = k2w_walk_kernel<RPL>;
     const size_t smem = wb * wpc;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long walkers = (long long)sm_count * wpc;
-    long long chunk = n / (walkers * 8);
-    if (chunk > 4096) chunk = 4096;
+    static const long long chunk_env = getenv("PPGPU_K2W_ITEM") ? atoll(getenv("PPGPU_K2W_ITEM")) : 0;
+    // work items: small enough to balance (the first prefixes of a level own thousands of candidates each), large enough
+    // to keep most groups of a prefix together (measured on levels 4-5 of the 100x30x6 program: 1024 beats 2048 and 4096)
+    long long chunk = chunk_env > 0 ? chunk_env : n / (walkers * 12);
+    if (chunk > 1024) chunk = 1024;
     if (chunk < 128) chunk = 128;
     long long grid = (n + chunk * wpc - 1) / (chunk * wpc);
     if (grid > sm_count) grid = sm_count;
@@ -517,23 +654,29 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
     return cudaGetLastError();
 }
 
-// *handled == false: the walk is off for this program / level (no vertex dictionary, level too small, prefix too long)
+// *handled == false: the walk is off for this program / level (no vertex dictionary, prefix too long, dictionary too large)
 cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled) {
     *handled = false;
     static const int on = getenv("PPGPU_K2W") ? atoi(getenv("PPGPU_K2W")) : 1;
+    static const int regs_on = getenv("PPGPU_K2W_REG") ? atoi(getenv("PPGPU_K2W_REG")) : 0;
     if (!on || !P.wk_ok || k_act < 1 || k_act - 2 > K2W_MAXFIX || P.W > 4 || P.nfree > 64) return cudaSuccess;
     const int rpl = (P.wk_nb + 31) / 32;
-#define K2W_GO(R) return launch_k2w_t<R>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled)
+#define K2W_GO(D) return launch_k2w_t<D>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled)
+    // The register-resident dictionary (instantiated for the 100 x 30 x 6 bench program: 76 basic rows x 37 columns) is
+    // an EXPERIMENT, off by default (PPGPU_K2W_REG=1): 255 registers + 2 KB of spills, measured 2.6x slower per pivot than
+    // the shared-memory dictionary (1395 vs 535 ms on levels 4-5); kept because it decides identically and is the
+    // starting point for a leaner version
+    if (regs_on && rpl == 3 && P.wk_ld == 37) K2W_GO(K2wRegDict<3 K2W_COMMA 37>);
     switch (rpl) {
-        case 1: K2W_GO(1);
-        case 2: K2W_GO(2);
-        case 3: K2W_GO(3);
-        case 4: K2W_GO(4);
-        case 5: K2W_GO(5);
-        case 6: K2W_GO(6);
-        case 7: K2W_GO(7);
-        case 8: K2W_GO(8);
+        case 1: K2W_GO(K2wSmemDict<1>);
+        case 2: K2W_GO(K2wSmemDict<2>);
+        case 3: K2W_GO(K2wSmemDict<3>);
+        case 4: K2W_GO(K2wSmemDict<4>);
+        case 5: K2W_GO(K2wSmemDict<5>);
+        case 6: K2W_GO(K2wSmemDict<6>);
+        case 7: K2W_GO(K2wSmemDict<7>);
+        case 8: K2W_GO(K2wSmemDict<8>);
         default: return cudaSuccess;
     }
 #undef K2W_GO
