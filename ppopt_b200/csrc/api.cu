@@ -177,7 +177,13 @@ int ppgpu_root_level(ppgpu_program* p, uint64_t* d_masks, int64_t* h_count, ppgp
 // candidates of one ppgpu_level_eval call are processed in chunks of this many, so that the K2a -> K2 hand-over buffers
 // (one residual vector per uncertified candidate) stay bounded however large the level is
 static long long level_chunk() {
-    static const long long c = getenv("PPGPU_CHUNK") ? atoll(getenv("PPGPU_CHUNK")) : (1ll << 24);
+    static const long long c = getenv("PPGPU_CHUNK") ? atoll(getenv("PPGPU_CHUNK")) : (1ll << 22);
+    return c < 1024 ? 1024 : c;
+}
+// with the vertex walk in front, the relaxation leaves next to nothing for the hand-over: the level can be one launch
+// (one kernel tail per level instead of one per 2^22 candidates, and the walk's longest-first scheduling sees every prefix)
+static long long walk_chunk() {
+    static const long long c = getenv("PPGPU_WALK_CHUNK") ? atoll(getenv("PPGPU_WALK_CHUNK")) : (1ll << 27);
     return c < 1024 ? 1024 : c;
 }
 
@@ -210,7 +216,7 @@ static cudaError_t ensure_warm(ppgpu_program* p, long long cap, cudaStream_t st)
     if (cap <= p->warm_cap) return cudaSuccess;
     // two sizes only (small levels / full chunks), so a solve grows its buffers at most twice
     const long long full = 4096 + level_chunk() / 8;
-    const long long want = cap <= 65536 ? 65536 : (cap > full ? cap : full);
+    const long long want = cap <= 65536 ? 65536 : (cap > full ? cap : full);   // (walked launches: n / 64 <= 2^27 / 64 = 4 full)
     cudaError_t e = cudaStreamSynchronize(st);   // earlier launches may still read the old buffers
     if (e != cudaSuccess) return e;
     warm_release(p);
@@ -257,7 +263,8 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
         static const int iters = getenv("PPGPU_K2A_ITERS") ? atoi(getenv("PPGPU_K2A_ITERS")) : 96;
         if (iters > 0 && k_act >= 0) {
             if (warm_on) {
-                const long long cap = n < 4096 ? n : 4096 + n / 8;
+                const bool walked = k_act >= 1 && p->dev.wk_ok && p->k2w_min >= 0 && n >= p->k2w_min;
+                const long long cap = n < 4096 ? n : 4096 + n / (walked ? 64 : 8);
                 if ((e = ensure_warm(p, cap, st)) != cudaSuccess) return fail("warm-start buffers", e);
                 p->dev.warm_count = p->d_warm_count; p->dev.warm_resid = p->d_warm_resid;
                 p->dev.warm_idx = p->d_warm_idx; p->dev.warm_cap = cap;
@@ -299,7 +306,8 @@ int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32
                      int32_t stages, ppgpu_stream stream) {
     if (!p) return fail_msg("null argument");
     if (n <= 0) return 0;
-    const long long chunk = level_chunk();
+    const bool walk = (stages & 2) && !(stages & 8) && k_act >= 1 && p->dev.wk_ok && p->k2w_min >= 0 && n >= p->k2w_min;
+    const long long chunk = walk ? walk_chunk() : level_chunk();
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t nn = n - off < chunk ? n - off : chunk;
         const int rc = level_eval_chunk(p, d_masks + (size_t)off * p->dev.W, nn, k_act, d_status + off, stages,

@@ -111,7 +111,9 @@ __device__ __forceinline__ void k2w_reload_labels(const DevProgram& P, const K2w
 }
 
 // ---- storage policy A: the dictionary in SHARED memory (any size that fits), lanes over rows
-template <int RPL_>
+// LD_ > 0: the number of columns (wk_ld) is a compile-time constant (odd, so that it is its own row stride): the rank-1
+// update unrolls into immediate-offset LDS / DFMA / STS with no bounds checks
+template <int RPL_, int LD_ = 0>
 struct K2wSmemDict {
     static constexpr int RPL = RPL_;
     static constexpr bool IN_SMEM = true;
@@ -124,7 +126,8 @@ struct K2wSmemDict {
     }
     // right-hand side of basic row wi and its largest eligible coefficient (uniform results)
     __device__ __forceinline__ void target_scan(const K2wCtx& c, int wi, uint64_t fm, int lane, double& bi, double& wbest, int& j) {
-        const double* Di = c.D + (size_t)wi * c.lds;
+        const int lds = LD_ > 0 ? LD_ : c.lds;
+        const double* Di = c.D + (size_t)wi * lds;
         bi = Di[0];
         const bool degen = bi <= 1e-11;
         double best = 0.0; int bj = 0x7fffffff;
@@ -141,13 +144,14 @@ struct K2wSmemDict {
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
             const int r = lane + 32 * rr;
-            col[rr] = r < c.nb ? c.D[(size_t)r * c.lds + 1 + j] : 0.0;
-            beta[rr] = r < c.nb ? c.D[(size_t)r * c.lds] : 0.0;
+            const int lds = LD_ > 0 ? LD_ : c.lds;
+            col[rr] = r < c.nb ? c.D[(size_t)r * lds + 1 + j] : 0.0;
+            beta[rr] = r < c.nb ? c.D[(size_t)r * lds] : 0.0;
         }
     }
     // basic row l leaves, nonbasic column j enters.  Returns false (uniformly) when some basic slack ends below -K2W_NEG_OK.
     __device__ __forceinline__ bool pivot(const K2wCtx& c, int l, int j, int lane) {
-        const int cj = 1 + j, lds = c.lds, ld = c.ld, nb = c.nb;
+        const int cj = 1 + j, lds = LD_ > 0 ? LD_ : c.lds, ld = LD_ > 0 ? LD_ : c.ld, nb = c.nb;
         double* Dl = c.D + (size_t)l * lds;
         const double inv = k2w_rcp(Dl[cj]);
         __syncwarp();
@@ -165,25 +169,49 @@ struct K2wSmemDict {
         // rank-1 update in groups of G columns: every load of a group is issued before its first FMA (the compiler cannot
         // hoist a shared-memory load above a store to another row on its own: one exposed LDS latency per element otherwise)
         constexpr int G = 8;
-        for (int k0 = 0; k0 < ld; k0 += G) {
-            double qk[G], x[RPL][G];
+        if constexpr (LD_ > 0) {
+            static_for<(LD_ + G - 1) / G>([&](auto KK) {
+                constexpr int k0 = decltype(KK)::value * G;
+                constexpr int GN = (LD_ - k0) < G ? (LD_ - k0) : G;
+                double qk[GN], x[RPL][GN];
 #pragma unroll
-            for (int g = 0; g < G; ++g) qk[g] = (k0 + g < ld) ? q[k0 + g] : 0.0;
+                for (int g = 0; g < GN; ++g) qk[g] = q[k0 + g];
 #pragma unroll
-            for (int rr = 0; rr < RPL; ++rr)
+                for (int rr = 0; rr < RPL; ++rr)
 #pragma unroll
-                for (int g = 0; g < G; ++g) x[rr][g] = (k0 + g < ld) ? Dr[rr][k0 + g] : 0.0;
+                    for (int g = 0; g < GN; ++g) x[rr][g] = Dr[rr][k0 + g];
 #pragma unroll
-            for (int rr = 0; rr < RPL; ++rr)
+                for (int rr = 0; rr < RPL; ++rr)
 #pragma unroll
-                for (int g = 0; g < G; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
+                    for (int g = 0; g < GN; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
 #pragma unroll
-            for (int rr = 0; rr < RPL; ++rr)
-                if (colr[rr] != 0.0) {
+                for (int rr = 0; rr < RPL; ++rr)
+                    if (colr[rr] != 0.0) {
 #pragma unroll
-                    for (int g = 0; g < G; ++g)
-                        if (k0 + g < ld) Dr[rr][k0 + g] = x[rr][g];
-                }
+                        for (int g = 0; g < GN; ++g) Dr[rr][k0 + g] = x[rr][g];
+                    }
+            });
+        } else {
+            for (int k0 = 0; k0 < ld; k0 += G) {
+                double qk[G], x[RPL][G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) qk[g] = (k0 + g < ld) ? q[k0 + g] : 0.0;
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) x[rr][g] = (k0 + g < ld) ? Dr[rr][k0 + g] : 0.0;
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
+#pragma unroll
+                for (int rr = 0; rr < RPL; ++rr)
+                    if (colr[rr] != 0.0) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            if (k0 + g < ld) Dr[rr][k0 + g] = x[rr][g];
+                    }
+            }
         }
         bool ok = true;
 #pragma unroll
@@ -314,7 +342,9 @@ __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict
     for (int w2 = 0; w2 < w; ++w2) rank += __popcll(c.orig[(size_t)a * c.W4 + w2]);
     rank += __popcll(c.orig[(size_t)a * c.W4 + w] & ((1ull << (b & 63)) - 1ull));
     const long long idx = seg_base + c.rowstart[a] + rank;
-    status[idx] = status[idx] | PPG_ST_FEAS;
+    // fire-and-forget OR on the aligned word that holds the byte (a load + store would stall the walker for an L2 round trip)
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(status + idx);
+    atomicOr(reinterpret_cast<unsigned*>(addr & ~(uintptr_t)3), (unsigned)PPG_ST_FEAS << (8u * (unsigned)(addr & 3)));
 }
 
 // marks every open candidate of the segment whose last two rows are nonbasic (full scan: after the prefix is fixed)
@@ -371,7 +401,7 @@ template <class Dict>
 __global__ void __launch_bounds__(256, 1)
 k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int chunk,
-                int walker_bytes, int lds, int W4) {
+                int walker_bytes, int lds, int W4, int group_items) {
     extern __shared__ unsigned char k2w_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int RPL = Dict::RPL;
@@ -432,13 +462,13 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
         if (c0 > 0) {
             uint64_t pfp[4]; int a_, b_;
             split(c0 - 1, pfp, a_, b_);
-            i = seg_end(c0, n, pfp, k_act >= 2 ? a_ : -1);
+            i = seg_end(c0, n, pfp, (group_items && k_act >= 2) ? a_ : -1);
         }
         if (i >= c1) continue;
         if (c1 < n) {
             uint64_t pfp[4]; int a_, b_;
             split(c1 - 1, pfp, a_, b_);
-            own_end = seg_end(c1, n, pfp, k_act >= 2 ? a_ : -1);
+            own_end = seg_end(c1, n, pfp, (group_items && k_act >= 2) ? a_ : -1);
         }
         dict.reload(P, c, lane);
         int npiv = 0, nfixed = 0;
@@ -649,7 +679,11 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
     long long grid = (n + chunk * wpc - 1) / (chunk * wpc);
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, 32 * wpc, smem, st>>>(P, masks, n, k_act, status, queue, counters, (int)chunk, (int)wb, lds, W4);
+    // ownership granularity: whole prefixes (all certificates of a vertex are used; the level is one launch and the long
+    // prefixes come first in lexicographic order, so the dynamic queue schedules longest-first) or (prefix, row) groups
+    static const int group_items = getenv("PPGPU_K2W_GROUPS") ? atoi(getenv("PPGPU_K2W_GROUPS")) : 0;
+    kern<<<(unsigned)grid, 32 * wpc, smem, st>>>(P, masks, n, k_act, status, queue, counters, (int)chunk, (int)wb, lds, W4,
+                                                 group_items);
     *handled = true;
     return cudaGetLastError();
 }
@@ -668,6 +702,7 @@ cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, 
     // the shared-memory dictionary (1395 vs 535 ms on levels 4-5); kept because it decides identically and is the
     // starting point for a leaner version
     if (regs_on && rpl == 3 && P.wk_ld == 37) K2W_GO(K2wRegDict<3 K2W_COMMA 37>);
+    if (rpl == 3 && P.wk_ld == 37) K2W_GO(K2wSmemDict<3 K2W_COMMA 37>);   // the bench shape, columns known at compile time
     switch (rpl) {
         case 1: K2W_GO(K2wSmemDict<1>);
         case 2: K2W_GO(K2wSmemDict<2>);
