@@ -64,9 +64,9 @@ k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long 
     if (!pd) { status[idx] = st | PPG_ST_PRE; return; }  // let the warp kernel report the numeric failure
     bool reject = false;
     // one right-hand side (column of V) at a time keeps the register footprint at KC doubles
-    double ub[KC], mx[KC], mag[KC];
+    double ub[KC], mx[KC], mag[KC], cst[KC];
 #pragma unroll
-    for (int a = 0; a < KC; ++a) { ub[a] = 0.0; mx[a] = 0.0; mag[a] = 0.0; }
+    for (int a = 0; a < KC; ++a) { ub[a] = 0.0; mx[a] = 0.0; mag[a] = 0.0; cst[a] = 0.0; }
     for (int c = 0; c < t1; ++c) {
         double x[KC];
 #pragma unroll
@@ -85,7 +85,7 @@ k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long 
         }
         if (c == 0) {
 #pragma unroll
-            for (int a = 0; a < KC; ++a) { ub[a] = x[a]; mag[a] = fabs(x[a]); }
+            for (int a = 0; a < KC; ++a) { ub[a] = x[a]; mag[a] = fabs(x[a]); cst[a] = x[a]; }
         } else {
             const double lo = __ldg(P.th_lo + c - 1), hi = __ldg(P.th_hi + c - 1);
 #pragma unroll
@@ -98,7 +98,13 @@ k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long 
     }
 #pragma unroll
     for (int a = 0; a < KC; ++a)
-        if (a < k && mx[a] > PPG_ZERO_ROW && ub[a] < -1e-9 * fmax(1.0, mag[a])) reject = true;
+        if (a < k) {
+            if (mx[a] > PPG_ZERO_ROW) { if (ub[a] < -1e-9 * fmax(1.0, mag[a])) reject = true; }
+            // a multiplier that does not depend on theta and is negative: the zero-row rule of the row build (numerically zero
+            // row with rhs < -1e-7 => not optimal, mpqp_utils.py:123-125 + the LP) applied before any row is built - 8 % of the
+            // level at the 100 x 30 x 6 program (active sets made of box rows only)
+            else if (mx[a] <= PPG_ZERO_ROW && cst[a] < -PPG_FEAS_TOL) reject = true;
+        }
     (void)t;
     if (!reject) status[idx] = st | PPG_ST_PRE;
 }
@@ -229,7 +235,8 @@ k34_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_
                     mx = fmax(mx, fabs(a));
                     if (a != 0.0) { const double term = fmax(a * lo, a * hi); ub += term; mag += fabs(term); }
                 }
-                if (mx > PPG_ZERO_ROW && ub < -1e-9 * fmax(1.0, mag)) reject = true;
+                if (mx > PPG_ZERO_ROW) { if (ub < -1e-9 * fmax(1.0, mag)) reject = true; }
+                else if (mx <= PPG_ZERO_ROW && Lam[j * t1] < -PPG_FEAS_TOL) reject = true;   // zero-row rule, see k3_prefilter_kernel
             }
             if (__any_sync(PPG_FULL, reject)) {
                 if (use_pre && lane == 0) status[idx] = st;
@@ -379,6 +386,13 @@ cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, 
     cudaError_t perr;
     const int use_pre = launch_k3p(P, masks, n, k_act, status, st, &perr) ? 1 : 0;
     if (perr != cudaSuccess) return perr;
+    {
+        // production path: the compact shared-memory form (k34c_compact.cu); the register form below is kept for programs
+        // whose tableau does not fit shared memory and as the A/B reference (PPGPU_K34_COMPACT=0)
+        bool handled = false;
+        const cudaError_t e = launch_k34_compact(P, masks, n, k_act, status, queue, counters, sm_count, st, use_pre, &handled);
+        if (e != cudaSuccess || handled) return e;
+    }
     if (P.t + 2 <= 8) { K34_RPT_SWITCH(8) }
     if (P.t + 2 <= 16) { K34_RPT_SWITCH(16) }
     return cudaErrorInvalidValue;

@@ -23,6 +23,9 @@ cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, 
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled);
 cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st);
+cudaError_t launch_k34_compact(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                               unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st,
+                               int use_pre, bool* handled);
 // general (LU) path: marks every feasible candidate that the reference would hand to check_optimality
 cudaError_t launch_mark_general(const DevProgram& P, long long n, int k_act, uint8_t* status, cudaStream_t st);
 

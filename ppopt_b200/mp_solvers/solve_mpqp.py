@@ -1,13 +1,14 @@
 """Dispatch with the reference's surface (/root/reference/src/ppopt/mp_solvers/solve_mpqp.py:23-114).
 
-Only the combinatorial algorithm is in scope (BASELINE.json north_star); the enum keeps the reference's member names so
+The combinatorial algorithm is the scope (BASELINE.json north_star), the two connected-graph algorithms ride on the same
+kernels; the enum keeps the reference's member names so
 that calling code type-checks, and every other member raises NotImplementedError instead of silently returning an
 empty solution."""
 from enum import Enum
 
 import numpy
 
-from . import mpqp_combi_graph, mpqp_combinatorial
+from . import mpqp_combi_graph, mpqp_combinatorial, mpqp_graph
 
 
 class mpqp_algorithm(Enum):
@@ -39,10 +40,17 @@ def solve_mpqp(problem, algorithm: mpqp_algorithm = mpqp_algorithm.combinatorial
                         f"With the following choices\n{mpqp_algorithm.all_algos()}")
     if algorithm is mpqp_algorithm.combinatorial_graph:
         solution = mpqp_combi_graph.solve(problem)          # solve_mpqp.py:100-101
-    elif algorithm is mpqp_algorithm.combinatorial:
-        solution = mpqp_combinatorial.solve(problem)        # solve_mpqp.py:70-71
+    elif algorithm in (mpqp_algorithm.combinatorial, mpqp_algorithm.combinatorial_parallel,
+                       mpqp_algorithm.combinatorial_parallel_exp):
+        # solve_mpqp.py:70-77: the reference's pool-parallel variants enumerate the same levels with the same per-candidate
+        # work (mpqp_parrallel_combinatorial.py:67-150); here every level is one GPU batch anyway
+        solution = mpqp_combinatorial.solve(problem)
+    elif algorithm is mpqp_algorithm.graph:
+        solution = mpqp_graph.solve(problem)                # solve_mpqp.py:79-80
+    elif algorithm is mpqp_algorithm.graph_exp:
+        solution = mpqp_graph.solve(problem, use_pruning=False)   # solve_mpqp.py:82-83
     else:
-        raise NotImplementedError(f'{algorithm} is outside the scope of the B200 engine (combinatorial, combinatorial_graph)')
+        raise NotImplementedError(f'{algorithm} is outside the scope of the B200 engine (combinatorial*, combinatorial_graph, graph, graph_exp)')
     # overlap flags exactly as the reference sets them (solve_mpqp.py:105-112)
     if hasattr(problem, 'Q') and problem.Q is not None:
         if min(numpy.linalg.eigvalsh(problem.Q)) <= 0:
