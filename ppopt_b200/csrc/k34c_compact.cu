@@ -27,6 +27,14 @@ struct K4cOut { int code; double beta; int pivots; long long work; };
 
 // Chebyshev LP of one candidate on the warp's shared-memory tableau.  Tab: m x lds, column 0 = rhs, 1..t = theta, t+1 = r.
 // flag[i]: 1 live row (basic slack), 0 dead.  Uniform result.
+// 1 / x to full double precision without the IEEE division sequence (x: a pivot / ratio denominator, normal and non-zero)
+__device__ __forceinline__ double k4c_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    return r * fma(-x, r, 2.0);
+}
+
 __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char* __restrict__ flag, int* __restrict__ bvar,
                                          double* __restrict__ alpha, int* __restrict__ kind, int* __restrict__ nbv,
                                          double* __restrict__ prow, int m, int t, int lds, double thr, int lane) {
@@ -34,8 +42,10 @@ __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char
     const int ld = nc + 1;
     K4cOut out; out.code = PPG_LP_OPTIMAL; out.beta = -CUDART_INF; out.pivots = 0; out.work = 0;
     int live = 0;
+    #pragma unroll 1
     for (int i = lane; i < m; i += 32) { bvar[i] = ld + i; live += flag[i] ? 1 : 0; }
     live = __reduce_add_sync(PPG_FULL, live);
+    #pragma unroll 1
     for (int c = lane; c < ld; c += 32) { alpha[c] = 0.0; kind[c] = (c >= 1) ? 1 : 0; nbv[c] = c; }   // kind: 1 free, 2 slack
     __syncwarp();
     double beta = 0.0;
@@ -46,6 +56,7 @@ __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char
         if (it == 0) {
             // r enters on the row of smallest right-hand side (whatever its sign): afterwards every slack is >= 0
             double mn = CUDART_INF; int r0 = 0x7fffffff;
+            #pragma unroll 1
             for (int i = lane; i < m; i += 32)
                 if (flag[i]) { const double v = Tab[(size_t)i * lds]; if (v < mn) { mn = v; r0 = i; } }
             warp_argmin(mn, r0);
@@ -59,6 +70,7 @@ __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char
             if (it > cap) { out.code = PPG_LP_ITERLIM; return out; }
             // ---- pricing (lanes over columns)
             double sc = 0.0; int key = 0x7fffffff, jc = 0x7fffffff;
+            #pragma unroll 1
             for (int c = 1 + lane; c < ld; c += 32) {
                 const double a = alpha[c];
                 const double s2 = kind[c] == 1 ? fabs(a) : (kind[c] == 2 ? -a : 0.0);
@@ -80,22 +92,24 @@ __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char
             dir = (entering_free && aj > 0.0) ? -1.0 : 1.0;
             // ---- Harris ratio test (lanes over rows)
             double hb = CUDART_INF;
+            #pragma unroll 1
             for (int i = lane; i < m; i += 32) {
                 if (!flag[i]) continue;
                 const double cv = dir * Tab[(size_t)i * lds + j];
                 if (cv > PPG_TINY) {
                     const double rhs = fmax(Tab[(size_t)i * lds], 0.0);
-                    hb = fmin(hb, (rhs + PPG_HARRIS) / cv);
+                    hb = fmin(hb, (rhs + PPG_HARRIS) * k4c_rcp(cv));
                 }
             }
             hb = warp_min_nonneg(hb);
             if (hb == CUDART_INF) { out.code = PPG_LP_UNBOUNDED; out.beta = CUDART_INF; return out; }
             double lp = 0.0, lr = CUDART_INF; int lrow = 0x7fffffff, lb = 0x7fffffff;
+            #pragma unroll 1
             for (int i = lane; i < m; i += 32) {
                 if (!flag[i]) continue;
                 const double cv = dir * Tab[(size_t)i * lds + j];
                 if (cv > PPG_TINY) {
-                    const double rat = fmax(Tab[(size_t)i * lds], 0.0) / cv;
+                    const double rat = fmax(Tab[(size_t)i * lds], 0.0) * k4c_rcp(cv);
                     if (rat <= hb) {
                         const bool better = bland ? (bvar[i] < lb) : (cv > lp);
                         if (better) { lp = cv; lrow = i; lb = bvar[i]; lr = rat; }
@@ -116,16 +130,19 @@ __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char
         // ---- Gauss-Jordan exchange (row l, column j)
         const bool entering_free = kind[j] == 1;
         double* Tl = Tab + (size_t)l * lds;
-        const double inv = 1.0 / Tl[j];
+        const double inv = k4c_rcp(Tl[j]);
         __syncwarp();
+        #pragma unroll 1
         for (int c = lane; c < ld; c += 32) prow[c] = (c == j) ? 0.0 : Tl[c] * inv;
         __syncwarp();
         const double aj = alpha[j];
+        #pragma unroll 1
         for (int i = lane; i < m; i += 32) {
             if (!flag[i] || i == l) continue;
             double* Ti = Tab + (size_t)i * lds;
             const double col = Ti[j];
             if (col != 0.0) {
+                #pragma unroll 1
                 for (int c = 0; c < ld; ++c) Ti[c] = fma(-col, prow[c], Ti[c]);
                 Ti[j] = -col * inv;
             }
@@ -133,7 +150,9 @@ __device__ __noinline__ K4cOut k4c_solve(double* __restrict__ Tab, unsigned char
         }
         __syncwarp();
         beta = fma(-aj, prow[0], beta);
+        #pragma unroll 1
         for (int c = 1 + lane; c < ld; c += 32) alpha[c] = (c == j) ? -aj * inv : fma(-aj, prow[c], alpha[c]);
+        #pragma unroll 1
         for (int c = lane; c < ld; c += 32) Tl[c] = (c == j) ? inv : prow[c];
         out.pivots++; out.work += (long long)live * (nc + 1);
         if (lane == 0) {
@@ -182,8 +201,10 @@ k34c_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k
             if (use_pre) st &= (uint8_t)~PPG_ST_PRE;
             const uint64_t* mk = masks + idx * W;
             __syncwarp();
+            #pragma unroll 1
             for (int j = lane; j < k; j += 32) act[j] = mask_nth(mk, W, j);
             __syncwarp();
+            #pragma unroll 1
             for (int e = lane; e < k * k; e += 32) {
                 const int a = e / k, b2 = e - a * k;
                 S[e] = __ldg(P.G + (size_t)act[a] * mi + act[b2]);
@@ -191,16 +212,20 @@ k34c_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k
             __syncwarp();
             // Cholesky (lower), right-looking, lanes over rows
             bool pd = true;
+            #pragma unroll 1
             for (int j = 0; j < k; ++j) {
                 const double d = S[j * k + j];
                 if (!(d > 0.0)) { pd = false; break; }
                 const double sd = sqrt(d);
                 __syncwarp();
+                #pragma unroll 1
                 for (int i = j + 1 + lane; i < k; i += 32) S[i * k + j] /= sd;
                 if (lane == 0) S[j * k + j] = sd;
                 __syncwarp();
+                #pragma unroll 1
                 for (int i = j + 1 + lane; i < k; i += 32) {
                     const double lij = S[i * k + j];
+                    #pragma unroll 1
                     for (int c = j + 1; c <= i; ++c) S[i * k + c] = fma(-lij, S[c * k + j], S[i * k + c]);
                 }
                 __syncwarp();
@@ -211,13 +236,17 @@ k34c_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k
             } else {
                 // Lambda = -S^-1 V[act]; lane c handles rhs column c (0 = constant term)
                 if (lane < t1) {
+                    #pragma unroll 1
                     for (int i = 0; i < k; ++i) {
                         double s = -__ldg(P.V + (size_t)act[i] * t1 + lane);
+                        #pragma unroll 1
                         for (int j = 0; j < i; ++j) s = fma(-S[i * k + j], Lam[j * t1 + lane], s);
                         Lam[i * t1 + lane] = s / S[i * k + i];
                     }
+                    #pragma unroll 1
                     for (int i = k - 1; i >= 0; --i) {
                         double s = Lam[i * t1 + lane];
+                        #pragma unroll 1
                         for (int j = i + 1; j < k; ++j) s = fma(-S[j * k + i], Lam[j * t1 + lane], s);
                         Lam[i * t1 + lane] = s / S[i * k + i];
                     }
@@ -225,8 +254,10 @@ k34c_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k
                 __syncwarp();
                 // necessary condition (see k34_kkt.cu): every nonzero multiplier row must reach lambda_j(theta) >= 0 in the box
                 bool reject = false;
+                #pragma unroll 1
                 for (int j = lane; j < k; j += 32) {
                     double ub = Lam[j * t1], mx = 0.0, mag = fabs(Lam[j * t1]);
+                    #pragma unroll 1
                     for (int c = 0; c < t; ++c) {
                         const double a = Lam[j * t1 + 1 + c];
                         const double lo = __ldg(P.th_lo + c), hi = __ldg(P.th_hi + c);
@@ -243,33 +274,42 @@ k34c_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k
                 // region rows into the tableau: [f | a | 1]
                 bool zero_viol = false;
                 double lo1 = -CUDART_INF, hi1 = CUDART_INF;
+                #pragma unroll 1
                 for (int row = lane; row < m; row += 32) {
                     double* T = Tab + (size_t)row * lds;
                     if (row < mi) {
                         if (mask_test(mk, row)) {
                             const int pos = mask_rank(mk, row);
                             T[0] = Lam[pos * t1];
+                            #pragma unroll 1
                             for (int c = 1; c < t1; ++c) T[c] = -Lam[pos * t1 + c];
                         } else {
+                            #pragma unroll 1
                             for (int c = 0; c < t1; ++c) T[c] = __ldg(P.V + (size_t)row * t1 + c);
+                            #pragma unroll 1
                             for (int a = 0; a < k; ++a) {
                                 // G is symmetric: G[act[a]][row] instead of G[row][act[a]] - consecutive lanes read
                                 // consecutive doubles of ONE row of G (8 sectors per warp load instead of 32)
                                 const double g = __ldg(P.G + (size_t)act[a] * mi + row);
+                                #pragma unroll 1
                                 for (int c = 0; c < t1; ++c) T[c] = fma(g, Lam[a * t1 + c], T[c]);
                             }
+                            #pragma unroll 1
                             for (int c = 1; c < t1; ++c) T[c] = -T[c];
                         }
                     } else {
                         const int o = row - mi;
                         T[0] = __ldg(P.b_t + o);
+                        #pragma unroll 1
                         for (int c = 1; c < t1; ++c) T[c] = __ldg(P.A_t + (size_t)o * t + c - 1);
                     }
                     double mx = 0.0, nn = 0.0;
+                    #pragma unroll 1
                     for (int c = 1; c < t1; ++c) { mx = fmax(mx, fabs(T[c])); nn = fma(T[c], T[c], nn); }
                     unsigned char fl = 0;
                     if (!(mx <= PPG_ZERO_ROW)) {
                         const double inv = 1.0 / sqrt(nn);
+                        #pragma unroll 1
                         for (int c = 0; c < t1; ++c) T[c] *= inv;
                         T[t1] = 1.0;
                         fl = 1;
