@@ -406,7 +406,9 @@ def run_gpu(args, rank, world, local_rank):
     value = units * len(ms_dev) / (sum(ms_dev) * 1e-3)
     e2e_value = units * len(ms_e2e) / (sum(ms_e2e) * 1e-3)
     # dominant kernel family of the timed steps and its in-kernel count of useful fp64 FMAs
-    fams = {'k2a_relax': ('k2p_relax_kernel (feasibility certificates, prefix-projected Gram in shared memory)', counters['k2a_work'], counters['k2a_tried']),
+    fams = {'k2w_walk': ('k2w_walk_kernel (feasibility certificates shared between the candidates of a prefix by a primal-simplex '
+                         'walk over vertices, slack dictionary in shared memory)', counters['k2w_work'], counters['k2w_certified']),
+            'k2a_relax': ('k2p_relax_kernel (feasibility certificates, prefix-projected Gram in shared memory)', counters['k2a_work'], counters['k2a_tried']),
             'k2_feas_lp': ('k2_feas_kernel (feasibility simplex)', counters['k2_work'], counters['k2_lps']),
             'k34_kkt_cheb': ('k34_kernel (KKT + Chebyshev screen)', counters['k4_work'], counters['k4_lps'])}
     dom = max(fams, key=lambda f: prof[f]['ms'])
@@ -422,7 +424,7 @@ def run_gpu(args, rank, world, local_rank):
         pass
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r02_k2p_traffic.json'))).get('dram_bytes_per_launch')
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', f'r02_{dom}_traffic.json'))).get('dram_bytes_per_launch')
     except Exception:
         pass
     line = {
@@ -439,14 +441,16 @@ def run_gpu(args, rank, world, local_rank):
         'roofline': {'kernel': dom_name, 'bound': 'fp64', 'achieved': k2_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                      'frac': k2_tflops / fp64_peak if fp64_peak else None, 'traffic': traffic,
                      'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this '
-                                       'kernel at level 4 (profiles/r02_k2p_traffic.json); ncu cannot run inside the timed run',
+                                       f'kernel (profiles/r02_{dom}_traffic.json, which names the launch); ncu cannot run inside '
+                                       'the timed run',
                      'peak_source': 'measured on this device: register-resident DFMA loop (ppgpu_measure_fp64_peak); '
                                     'MEASURED_PEAKS.json carries no fp64 figure',
                      'launches': k2['launches'], 'avg_launch_ms': k2['ms'] / max(1, k2['launches']),
                      'flops_per_launch': k2_flops / max(1, k2['launches']), 'units': dom_units,
                      'share_of_step': k2['ms'] / max(1e-9, sum(v['ms'] for v in prof.values())),
-                     'flop_model': 'useful fp64 FMAs counted in-kernel: K2a relaxation steps x R0 x 3 (row update with the two '
-                                   'suffix rows deflated; the prefix projection is paid once per prefix); K2/K4 pivots x live rows x columns',
+                     'flop_model': 'useful fp64 FMAs counted in-kernel: K2w pivots x basic rows x columns of the slack dictionary '
+                                   '(rank-1 update); K2a relaxation steps x R0 x 3; K2/K4 pivots x live rows x columns',
+                     'k2w': {'certified': counters['k2w_certified'], 'pivots': counters['k2w_pivots'], 'gave_up': counters['k2w_giveup']},
                      'k2a': {'tried': counters['k2a_tried'], 'certified': counters['k2a_certified'], 'steps': counters['k2a_steps']},
                      'k2': {'lps': counters['k2_lps'], 'pivots': counters['k2_pivots']},
                      'hbm': {'achieved': hbm_bytes / max(k2['ms'] * 1e-3, 1e-12) / 1e9, 'peak': peaks.get('hbm_gbs'),
