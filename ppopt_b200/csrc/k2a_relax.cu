@@ -227,7 +227,7 @@ static cudaError_t launch_k2a_t(const DevProgram& P, const uint64_t* masks, long
     const size_t smem = per_warp * 4 * sizeof(double);
     cudaError_t e;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_max_smem(kern);
         if (e != cudaSuccess) return e;
     }
     int occ = 0;

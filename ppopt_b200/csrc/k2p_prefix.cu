@@ -554,7 +554,7 @@ static cudaError_t launch_k2p_t(const DevProgram& P, const uint64_t* masks, long
     const size_t smem = ((size_t)P.R0 * LD + LD + scratch) * sizeof(double) + (size_t)K2P_CHUNK * P.W * 8 + (size_t)K2P_CHUNK * 4 +
                         (size_t)(THREADS / 32) * ((LD + 31) / 32) * 32 * sizeof(double);
     if (smem > 220 * 1024) { *handled = false; return cudaSuccess; }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem(kern);
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);

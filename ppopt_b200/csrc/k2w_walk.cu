@@ -667,7 +667,7 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
     if (wpc > 8) wpc = 8;
     if (wpc < 1) return cudaSuccess;   // dictionary too large for shared memory: the relaxation handles the level
     const size_t smem = wb * wpc;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = allow_max_smem(kern);
     if (e != cudaSuccess) return e;
     const long long walkers = (long long)sm_count * wpc;
     static const long long chunk_env = getenv("PPGPU_K2W_ITEM") ? atoll(getenv("PPGPU_K2W_ITEM")) : 0;

@@ -369,7 +369,7 @@ cudaError_t launch_k34_compact(const DevProgram& P, const uint64_t* masks, long 
     wb = (wb + 15) & ~(size_t)15;
     const size_t smem = wb * WPC;
     if (smem > 200 * 1024) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k34c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem(k34c_kernel);
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k34c_kernel, 32 * WPC, smem);

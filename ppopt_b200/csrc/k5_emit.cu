@@ -349,7 +349,7 @@ static cudaError_t launch_k5_t(const DevProgram& P, const uint64_t* masks, const
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_max_smem(kern);
         if (e != cudaSuccess) return e;
     }
     long long grid = n_sel;

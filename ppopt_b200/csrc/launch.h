@@ -7,6 +7,20 @@
 
 namespace ppgpu {
 
+// Opt a kernel in to the device's full dynamic shared memory.  Always the SAME value: cudaFuncSetAttribute is per function
+// and process wide, and handles are driven from several host threads at once (mpMIQP sub-problems on their own streams) -
+// setting the size of the launch at hand let one thread shrink the limit under another thread's launch.
+template <class K>
+inline cudaError_t allow_max_smem(K kern) {
+    int dev = 0, lim = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - (int)fa.sharedSizeBytes);   // static + dynamic <= limit
+}
+
 int k2_pad_columns(int ncols_with_rhs);
 
 cudaError_t launch_k1(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
