@@ -137,6 +137,16 @@ int ppgpu_locate_points(const double* d_theta, int64_t n_points, int32_t t, cons
                         const double* d_Q, const double* d_H, const double* d_c, int32_t* d_region, double* d_x,
                         ppgpu_stream stream);
 
+/* Batched Chebyshev balls of polytopes {theta : E theta <= f} (chebyshev_ball, utils/chebyshev_ball.py:10-63: max r subject to
+ * E_i theta + |E_i| r <= f_i): CriticalRegion.is_full_dimension (critical_region.py:89-105, radius > 1e-8) and the Chebyshev /
+ * feasibility checks of the program constructor's warnings() (mplp_program.py:162-215).  Stateless - no program handle.
+ *   d_rows     total_rows x (t + 1)   stacked rows [f | E] of all polytopes
+ *   d_row_off  n_polytopes + 1        first row of every polytope;  max_rows = the largest row count
+ *   d_radius   n_polytopes            Chebyshev radius (+inf: unbounded, -inf: empty because of a row 0 <= f < 0)
+ *   d_code     n_polytopes int32      PPG_LP_* of csrc/tolerances.h (0 optimal, 2 unbounded, 3 empty, 4 iteration limit) */
+int ppgpu_chebyshev_batch(const double* d_rows, const int64_t* d_row_off, int64_t n_polytopes, int32_t t, int32_t max_rows,
+                          double* d_radius, int32_t* d_code, ppgpu_stream stream);
+
 /* cumulative device counters (LPs, pivots, useful FMAs per kernel family, borderline/numeric flags) */
 int ppgpu_counters(ppgpu_program* prog, uint64_t* h_out, int32_t reset, ppgpu_stream stream);
 

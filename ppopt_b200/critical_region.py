@@ -40,5 +40,11 @@ class CriticalRegion:
     def is_inside(self, theta, tol=1e-5) -> bool:
         return bool((self.E @ theta - self.f < tol).all())
 
+    def is_full_dimension(self) -> bool:
+        """Chebyshev radius of {theta : E theta <= f} > 1e-8 (critical_region.py:89-105), one small LP on the GPU; use
+        ppopt_b200.chebyshev.full_dimensional(regions) to test many regions in one launch"""
+        from .chebyshev import RADIUS_TOL, chebyshev_radii
+        return bool(chebyshev_radii([(self.E, self.f)])[0] > RADIUS_TOL)
+
     def get_constraints(self):
         return [self.E, self.f]

@@ -106,6 +106,17 @@ int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, 
     if (k2_pad_columns(R.nfree + 2) < 0) { delete p; return fail_msg("n - n_eq + t + 2 > 64 columns are not supported"); }
     if (R.t + 2 > 16) { delete p; return fail_msg("more than 14 parameters are not supported"); }
     if (R.np > 64) { delete p; return fail_msg("n - n_eq > 64 is not supported"); }
+    {
+        // region emission (K5) factors the (n + k) x (n + k) KKT matrix of a candidate in shared memory: check the deepest level
+        // now instead of failing with "invalid argument" in the middle of a solve (k5_emit.cu::launch_k5_t)
+        const int depth = (R.n > R.t ? R.n : R.t) - R.ne, k = R.ne + (depth > 0 ? depth : 0), N = R.n + k, ld = N + R.t + 1;
+        const size_t smem = ((size_t)N * ld + (size_t)R.R0 * (R.t + 1)) * sizeof(double) + (size_t)(2 * R.R0 + k + 2) * sizeof(int);
+        if (smem > 200 * 1024) {
+            delete p;
+            return fail_msg("region emission needs " + std::to_string(smem / 1024) + " KB of shared memory at the deepest level (n + k = " +
+                            std::to_string(N) + "); the limit is 200 KB (about n + k <= 150)");
+        }
+    }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete p; return fail("cudaSetDevice", e); }
     p->device = device;
@@ -503,6 +514,22 @@ int ppgpu_locate_points(const double* d_theta, int64_t n_points, int32_t t, cons
     e = launch_locate(d_theta, n_points, t, d_rows, (const long long*)d_row_off, n_regions, d_laws, n_x, use_tol, tol,
                       overlap ? 1 : 0, d_Q, d_H, d_c, d_region, d_x, sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("K7 point location", e);
+    return 0;
+}
+
+int ppgpu_chebyshev_batch(const double* d_rows, const int64_t* d_row_off, int64_t n_polytopes, int32_t t, int32_t max_rows,
+                          double* d_radius, int32_t* d_code, ppgpu_stream stream) {
+    if (n_polytopes < 0) return fail_msg("negative size");
+    if (n_polytopes == 0) return 0;
+    if (!d_rows || !d_row_off || !d_radius || !d_code) return fail_msg("null argument");
+    if (t < 1 || t > 30) return fail_msg("the Chebyshev batch supports 1 <= t <= 30 parameters");
+    if (max_rows < 1 || max_rows > 1024) return fail_msg("the Chebyshev batch supports 1..1024 rows per polytope");
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail("device query", e);
+    e = launch_cheb_batch(d_rows, (const long long*)d_row_off, n_polytopes, t, max_rows, d_radius, d_code, sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("Chebyshev batch", e);
     return 0;
 }
 

@@ -384,4 +384,64 @@ cudaError_t launch_k34_compact(const DevProgram& P, const uint64_t* masks, long 
     return cudaGetLastError();
 }
 
+// ---- batched Chebyshev balls of arbitrary polytopes {theta : E theta <= f} (chebyshev_ball, utils/chebyshev_ball.py:10-63:
+// max r : E_i theta + |E_i| r <= f_i; CriticalRegion.is_full_dimension, critical_region.py:89-105; the constructor's
+// warnings(), mplp_program.py:162-215).  One warp per polytope, the LP of k4c_solve on the warp's shared-memory tableau.
+__global__ void __launch_bounds__(128)
+cheb_batch_kernel(const double* __restrict__ rows, const long long* __restrict__ row_off, long long n_poly, int t,
+                  double* __restrict__ radius, int* __restrict__ code, int warp_bytes, int lds, int max_rows) {
+    extern __shared__ unsigned char cheb_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t1 = t + 1;
+    unsigned char* base = cheb_smem + (size_t)warp * warp_bytes;
+    double* Tab = reinterpret_cast<double*>(base); base += (size_t)max_rows * lds * 8;
+    double* alpha = reinterpret_cast<double*>(base); base += (size_t)lds * 8;
+    double* prow = reinterpret_cast<double*>(base); base += (size_t)lds * 8;
+    int* bvar = reinterpret_cast<int*>(base); base += (size_t)((max_rows + 1) & ~1) * 4;
+    int* kind = reinterpret_cast<int*>(base); base += (size_t)((lds + 1) & ~1) * 4;
+    int* nbv = reinterpret_cast<int*>(base); base += (size_t)((lds + 1) & ~1) * 4;
+    unsigned char* flag = base;
+    for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + warp; p < n_poly; p += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const long long r0 = row_off[p];
+        const int m = (int)(row_off[p + 1] - r0);
+        bool bad = false;
+        __syncwarp();
+#pragma unroll 1
+        for (int i = lane; i < m; i += 32) {
+            const double* src = rows + (size_t)(r0 + i) * t1;
+            double* T = Tab + (size_t)i * lds;
+            double nn = 0.0;
+            T[0] = src[0];
+#pragma unroll 1
+            for (int c = 1; c < t1; ++c) { T[c] = src[c]; nn = fma(src[c], src[c], nn); }
+            T[t1] = sqrt(nn);
+            // a row without theta reads 0 <= f: either always true (dropped) or never (the polytope is empty)
+            flag[i] = nn > 0.0 ? 1 : 0;
+            if (!(nn > 0.0) && src[0] < 0.0) bad = true;
+        }
+        __syncwarp();
+        K4cOut res; res.code = PPG_LP_INFEAS_EQ; res.beta = -CUDART_INF;
+        if (!__any_sync(PPG_FULL, bad) && m > 0)
+            res = k4c_solve(Tab, flag, bvar, alpha, kind, nbv, prow, m, t, lds, CUDART_INF, lane);
+        if (lane == 0) { radius[p] = res.beta; code[p] = res.code; }
+    }
+}
+
+cudaError_t launch_cheb_batch(const double* rows, const long long* row_off, long long n_poly, int t, int max_rows,
+                              double* radius, int* code, int sm_count, cudaStream_t st) {
+    constexpr int WPC = 4;
+    const int ld = t + 2, lds = ld | 1;
+    size_t wb = (size_t)max_rows * lds * 8 + (size_t)2 * lds * 8 + (size_t)(((max_rows + 1) & ~1) + 2 * ((lds + 1) & ~1)) * 4 +
+                (size_t)max_rows;
+    wb = (wb + 15) & ~(size_t)15;
+    const size_t smem = wb * WPC;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = allow_max_smem(cheb_batch_kernel);
+    if (e != cudaSuccess) return e;
+    long long grid = (n_poly + WPC - 1) / WPC;
+    if (grid > (long long)sm_count * 4) grid = (long long)sm_count * 4;
+    if (grid < 1) return cudaSuccess;
+    cheb_batch_kernel<<<(unsigned)grid, 32 * WPC, smem, st>>>(rows, row_off, n_poly, t, radius, code, (int)wb, lds, max_rows);
+    return cudaGetLastError();
+}
+
 }  // namespace ppgpu

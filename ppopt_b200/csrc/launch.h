@@ -68,6 +68,8 @@ cudaError_t launch_locate(const double* theta, long long n_points, int t, const 
                           const double* Qm, const double* Hm, const double* cv, int* region_out, double* x_out, int sm_count,
                           cudaStream_t st);
 
+cudaError_t launch_cheb_batch(const double* rows, const long long* row_off, long long n_poly, int t, int max_rows,
+                              double* radius, int* code, int sm_count, cudaStream_t st);
 cudaError_t launch_clear_bits(uint8_t* status, long long n, uint8_t bits, cudaStream_t st);
 
 cudaError_t measure_fp64_peak(int iters, double* tflops, cudaStream_t st);

@@ -47,6 +47,33 @@ class MPLP_Program:
         self.A, self.b, self.F, self.A_t, self.b_t = [numpy.ascontiguousarray(x) for x in presolve.remove_redundant(
             self.A, self.b, self.F, self.A_t, self.b_t, n_eq)]
 
+    def warnings(self):
+        """The two numerical checks of the reference constructor's warnings() (mplp_program.py:204-215) on the GPU: the
+        Chebyshev ball of the (x, theta) feasible space and the feasibility of the program as stated.  (The shape checks of
+        :166-202 are raised as errors by this constructor.)"""
+        from .chebyshev import chebyshev_radii
+        out = []
+        n, t = self.A.shape[1], self.F.shape[1]
+        ne = len(self.equality_indices)
+        if ne == 0:
+            # (with equality rows the ball lives in their affine hull: chebyshev_ball gives those rows no radius term, the
+            # batched kernel has no equality rows, so that variant is only covered by the feasibility check below)
+            A_xt = numpy.vstack([numpy.hstack([self.A, -self.F]), numpy.hstack([numpy.zeros((self.A_t.shape[0], n)), self.A_t])])
+            b_xt = numpy.vstack([self.b.reshape(-1, 1), self.b_t.reshape(-1, 1)])
+            rad = chebyshev_radii([(A_xt, b_xt)])[0]
+            if not (rad > 0.0):
+                out.append('The chebychev ball has either a radius of zero, or the problem is not feasible!')
+        from . import engine as _engine
+        import torch
+        eng = _engine.Engine(_engine.program_arrays(self))
+        try:
+            m0 = torch.zeros((1, eng.W), dtype=torch.int64, device=eng.tdev)
+            if not (int(eng.level_eval(m0, 0, stages=3).cpu()[0]) & 2):
+                out.append('The multiparametric program, as stated, is not feasible!')
+        finally:
+            eng.close()
+        return out
+
     def num_x(self) -> int:
         return self.A.shape[1]
 
