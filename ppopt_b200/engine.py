@@ -245,35 +245,86 @@ def _region_classes(program):
     return CriticalRegion, Solution
 
 
-def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, info) -> list:
-    """CriticalRegion objects from K5's buffers (field meaning: mpqp_utils.py:181-195)."""
+def _to_host(x):
+    """device tensor -> numpy through a pinned staging buffer (torch caches pinned blocks); numpy arrays pass through"""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            h.copy_(x, non_blocking=True)
+            torch.cuda.current_stream(x.device).synchronize()
+            return h.numpy()
+        return x.numpy()
+    return numpy.asarray(x)
+
+
+def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, info, d2h: Optional[list] = None) -> list:
+    """CriticalRegion objects from K5's buffers (field meaning: mpqp_utils.py:181-195).  The buffers may be device tensors
+    (the solver's case) or numpy arrays.  Everything that can be done for the whole level at once is done on whole arrays -
+    on the DEVICE when the buffers are there: the law blocks are split into contiguous A, b, C, d, the kept half-spaces of
+    all regions are gathered with one boolean mask (only those rows cross PCIe: ~1/5 of the rows buffer), the kept-index
+    lists of all regions come from one nonzero - and per region only views and list slices remain.  At the bench workload
+    5,570 regions are assembled per solve; a Python loop over the constraints of every region cost more than the level-5
+    kernels.  ``d2h``: optional list that receives the number of bytes copied device -> host."""
     n, t, ne, m = eng.n, eng.t, eng.n_eq, eng.m
-    out = []
+    ns = len(active_sets)
+    if ns == 0:
+        return []
     n_inact = eng.mi - k_act
-    for si, aset in enumerate(active_sets):
-        if info[si, 0] != 1.0:
+    on_dev = isinstance(laws, torch.Tensor)
+    copied = 0
+
+    def host(x):
+        nonlocal copied
+        h = _to_host(x.contiguous() if isinstance(x, torch.Tensor) else numpy.ascontiguousarray(x))
+        copied += h.nbytes
+        return h
+    kept_all = (flags & 3) == 3                       # non-zero and non-redundant rows
+    nodup_all = kept_all & ((flags & 4) == 0)         # ... that are not duplicates of an earlier row
+    info = host(info)
+    emitted = (info[:, 0] == 1.0).tolist()
+    A_all, b_all = host(laws[:, :n, 1:]), host(laws[:, :n, :1])
+    C_all, d_all = host(laws[:, n:, 1:]), host(laws[:, n:, :1])
+    if t != 1:
+        # kept, de-duplicated half-spaces of every region, stacked; a region's block is a contiguous slice of it
+        E_cat, f_cat = host(rows[:, :, 1:][nodup_all]), host(rows[:, :, :1][nodup_all])
+        e_off = numpy.concatenate([[0], numpy.cumsum(host(nodup_all.sum(1)))]).tolist()
+    kept_all = host(kept_all)
+    asets = numpy.asarray(active_sets, dtype=numpy.int64).reshape(ns, ne + k_act)
+    aset_lists = asets.tolist()
+    # kept-index lists of every region: rows [0, k_act) are the multiplier rows (lambda_set: the constraint they belong to),
+    # [k_act, k_act + n_inact) the inactive constraints (regular_set: position, constraint), the rest the Theta rows (omega_set)
+    ri, ci = numpy.nonzero(kept_all)
+    bounds = numpy.searchsorted(ri, numpy.arange(ns + 1)).tolist()
+    is_l, is_r = ci < k_act, (ci >= k_act) & (ci < k_act + n_inact)
+    val = numpy.empty(ci.shape[0], dtype=numpy.int64)
+    val[is_l] = asets[ri[is_l], ne + ci[is_l]]
+    act_bool = numpy.zeros((ns, m), dtype=bool)
+    if asets.shape[1]:
+        act_bool[numpy.arange(ns)[:, None], asets] = True
+    if n_inact > 0:
+        inactive = numpy.nonzero(~act_bool)[1].reshape(ns, n_inact)
+        val[is_r] = inactive[ri[is_r], ci[is_r] - k_act]
+    val[~(is_l | is_r)] = ci[~(is_l | is_r)] - (k_act + n_inact)
+    n_l = numpy.searchsorted(ri[is_l], numpy.arange(ns + 1))
+    n_lr = numpy.searchsorted(ri[is_l | is_r], numpy.arange(ns + 1))
+    n_l, n_lr = (n_l[1:] - n_l[:-1]).tolist(), (n_lr[1:] - n_lr[:-1]).tolist()
+    val_list, pos_list = val.tolist(), (ci - k_act).tolist()
+    out = []
+    for si in range(ns):
+        if not emitted[si]:
             out.append(None)
             continue
-        law = laws[si]
-        fl = flags[si]
-        kept = numpy.nonzero((fl & 3) == 3)[0]
         if t == 1:
             E = numpy.array([[1], [-1]])
             f = numpy.array([[info[si, 3]], [-info[si, 2]]])
         else:
-            nd = numpy.nonzero(((fl & 3) == 3) & ((fl & 4) == 0))[0]
-            E = numpy.ascontiguousarray(rows[si][nd, 1:])
-            f = numpy.ascontiguousarray(rows[si][nd, :1])
-        active = aset[ne:]
-        aset_set = set(aset)
-        inactive = [i for i in range(m) if i not in aset_set]
-        lam = [active[i] for i in kept if i < k_act]
-        reg_pos = [int(i - k_act) for i in kept if k_act <= i < k_act + n_inact]
-        omega = [int(i - k_act - n_inact) for i in kept if i >= k_act + n_inact]
-        region = cr_cls(numpy.ascontiguousarray(law[:n, 1:]), numpy.ascontiguousarray(law[:n, :1]),
-                        numpy.ascontiguousarray(law[n:, 1:]), numpy.ascontiguousarray(law[n:, :1]), E, f, list(aset),
-                        omega, lam, [reg_pos, [inactive[p] for p in reg_pos]])
-        out.append(region)
+            E, f = E_cat[e_off[si]:e_off[si + 1]], f_cat[e_off[si]:e_off[si + 1]]
+        lo = bounds[si]
+        l_end, r_end, hi = lo + n_l[si], lo + n_lr[si], bounds[si + 1]
+        out.append(cr_cls(A_all[si], b_all[si], C_all[si], d_all[si], E, f, aset_lists[si], val_list[r_end:hi],
+                          val_list[lo:l_end], [pos_list[l_end:r_end], val_list[l_end:r_end]]))
+    if d2h is not None:
+        d2h.append(copied if on_dev else 0)
     return out
 
 
@@ -416,11 +467,11 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
                     mine, bufs = sharding.gather_regions(eng, mine, bufs, k_act, dist)
                     status = sharding.gather_region_bits(status, mine, dist, already_global=True, bufs=bufs)
                 if bufs is not None and mine.shape[0]:
-                    laws, rows, flags, info = [x.cpu().numpy() for x in bufs]
+                    laws, rows, flags, info = bufs
                     sel_masks = masks[mine].cpu().numpy()
-                    eng.d2h_bytes += laws.nbytes + rows.nbytes + flags.nbytes + info.nbytes + sel_masks.nbytes
+                    eng.d2h_bytes += sel_masks.nbytes
                     asets = eng.lists_from_masks(sel_masks)
-                    sing = numpy.nonzero(info[:, 0] < 0)[0]
+                    sing = torch.nonzero(info[:, 0] < 0).reshape(-1).cpu().numpy()
                     if sing.size:
                         if eng.use_gram or not eng.is_qp:
                             # passed the optimality screen and the KKT system is singular: what the reference raises
@@ -430,7 +481,9 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
                         # the reference only solves the KKT system of sets that passed check_optimality, so a singular
                         # system of an arbitrary feasible set is skipped and reported, not raised
                         flagged['singular_skipped'].extend(asets[i] for i in sing[:256])
-                    built = build_regions(eng, cr_cls, asets, k_act, laws, rows, flags, info)
+                    copied = []
+                    built = build_regions(eng, cr_cls, asets, k_act, laws, rows, flags, info, d2h=copied)
+                    eng.d2h_bytes += sum(copied)
                     regions.extend(r for r in built if r is not None)
             n_reg = int(((status & ST_REGION) != 0).sum().item())
         feas_idx = eng.select(status, ST_FEAS, ST_FEAS)
