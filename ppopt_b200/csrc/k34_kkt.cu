@@ -45,6 +45,8 @@ k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long 
 #pragma unroll
         for (int b = 0; b <= a; ++b) L[a][b] = (a < k && b < k) ? __ldg(P.G + (size_t)act[a] * mi + act[b]) : (a == b ? 1.0 : 0.0);
     bool pd = true;
+    double Linv[KC];   // 1 / L[j][j]: the 2 (t+1) KC substitutions below multiply instead of dividing (an fp64 division is ~25
+                       // instructions; they were a third of this kernel)
 #pragma unroll
     for (int j = 0; j < KC; ++j) {
         double d = L[j][j];
@@ -53,6 +55,7 @@ k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long 
         if (!(d > 0.0)) pd = false;
         const double sd = sqrt(d > 0.0 ? d : 1.0), isd = 1.0 / sd;
         L[j][j] = sd;
+        Linv[j] = isd;
 #pragma unroll
         for (int i = j + 1; i < KC; ++i) {
             double s2 = L[i][j];
@@ -74,14 +77,14 @@ k3_prefilter_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long 
             double s2 = (i < k) ? -__ldg(P.V + (size_t)act[i] * t1 + c) : 0.0;
 #pragma unroll
             for (int j = 0; j < i; ++j) s2 = fma(-L[i][j], x[j], s2);
-            x[i] = s2 / L[i][i];
+            x[i] = s2 * Linv[i];
         }
 #pragma unroll
         for (int i = KC - 1; i >= 0; --i) {
             double s2 = x[i];
 #pragma unroll
             for (int j = i + 1; j < KC; ++j) s2 = fma(-L[j][i], x[j], s2);
-            x[i] = s2 / L[i][i];
+            x[i] = s2 * Linv[i];
         }
         if (c == 0) {
 #pragma unroll
