@@ -45,7 +45,7 @@ struct K2wCtx {
     int* nvar;        // nf         row id nonbasic in column j
     int* where;       // R0         >= 0: dictionary row, < 0: ~column
     uint64_t* orig;   // R0 x W4    segment: bit b of row a = candidate P+{a,b} exists in the segment
-    uint64_t* todo;   // R0 x W4    ... and is still open
+    uint64_t* todo;   // R0 x W4    ... and is still open; symmetric (see k2w_mark_row)
     int* rowstart;    // R0         position in the segment of the first candidate with second-last row a
     uint64_t* nbm;    // W4         bitmask of the nonbasic rows
     int* fixrow;      // K2W_MAXFIX rows of the prefix currently fixed, in order
@@ -169,6 +169,7 @@ struct K2wSmemDict {
         // rank-1 update in groups of G columns: every load of a group is issued before its first FMA (the compiler cannot
         // hoist a shared-memory load above a store to another row on its own: one exposed LDS latency per element otherwise)
         constexpr int G = 8;
+        bool okb = true;
         if constexpr (LD_ > 0) {
             static_for<(LD_ + G - 1) / G>([&](auto KK) {
                 constexpr int k0 = decltype(KK)::value * G;
@@ -184,6 +185,14 @@ struct K2wSmemDict {
                 for (int rr = 0; rr < RPL; ++rr)
 #pragma unroll
                     for (int g = 0; g < GN; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
+                if constexpr (k0 == 0) {
+                    // column 0 is the right-hand side: the certification band is checked on the value just computed
+#pragma unroll
+                    for (int rr = 0; rr < RPL; ++rr) {
+                        const int r = lane + 32 * rr;
+                        okb = okb && (r >= nb || r == l || x[rr][0] >= -K2W_NEG_OK);
+                    }
+                }
 #pragma unroll
                 for (int rr = 0; rr < RPL; ++rr)
                     if (colr[rr] != 0.0) {
@@ -213,13 +222,13 @@ struct K2wSmemDict {
                     }
             }
         }
-        bool ok = true;
+        bool ok = okb;
 #pragma unroll
         for (int rr = 0; rr < RPL; ++rr) {
             const int r = lane + 32 * rr;
             if (r < nb && r != l) {
                 if (colr[rr] != 0.0) Dr[rr][cj] = -colr[rr] * inv;
-                ok = ok && Dr[rr][0] >= -K2W_NEG_OK;
+                if constexpr (LD_ == 0) ok = ok && Dr[rr][0] >= -K2W_NEG_OK;
             }
         }
         __syncwarp();
@@ -347,18 +356,29 @@ __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict
     atomicOr(reinterpret_cast<unsigned*>(addr & ~(uintptr_t)3), (unsigned)PPG_ST_FEAS << (8u * (unsigned)(addr & 3)));
 }
 
+// bits of word w with index >= a
+__device__ __forceinline__ uint64_t k2w_ge_mask(int a, int w) {
+    const int aw = a >> 6;
+    return w < aw ? 0ull : (w == aw ? (~0ull << (a & 63)) : ~0ull);
+}
+
+// Open candidates live in a SYMMETRIC bit matrix: bit y of row x is set while the candidate with last rows {x, y} is open
+// (single-row candidates: the diagonal).  The half with y >= x is canonical, the other half mirrors it so that "which open
+// candidates does row r belong to" is ONE row read (the mirror may lag behind: it is confirmed against the canonical bit).
+
 // marks every open candidate of the segment whose last two rows are nonbasic (full scan: after the prefix is fixed)
 __device__ __forceinline__ int k2w_mark_all(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int lane) {
     int got = 0;
     for (int a = lane; a < c.R0; a += 32) {
         if (!((c.nbm[a >> 6] >> (a & 63)) & 1ull)) continue;
         for (int w = 0; w < c.W4; ++w) {
-            uint64_t bits = c.nbm[w] & c.todo[(size_t)a * c.W4 + w];
+            uint64_t bits = c.nbm[w] & c.todo[(size_t)a * c.W4 + w] & k2w_ge_mask(a, w);
             if (!bits) continue;
-            c.todo[(size_t)a * c.W4 + w] &= ~bits;
+            atomicAnd(reinterpret_cast<unsigned long long*>(c.todo + (size_t)a * c.W4 + w), ~bits);
             while (bits) {
                 const int bb = w * 64 + __ffsll((long long)bits) - 1;
                 bits &= bits - 1ull;
+                if (bb != a) atomicAnd(reinterpret_cast<unsigned long long*>(c.todo + (size_t)bb * c.W4 + (a >> 6)), ~(1ull << (a & 63)));
                 k2w_certify(c, status, seg_base, a, bb);
                 ++got;
             }
@@ -367,30 +387,35 @@ __device__ __forceinline__ int k2w_mark_all(const K2wCtx& c, uint8_t* __restrict
     return got;
 }
 
-// after a pivot only the pairs with the row r that has just become nonbasic can be new: (r, b) and (a, r)
+// after a pivot only the candidates with the row r that has just become nonbasic can be new: one read of row r
 __device__ __forceinline__ int k2w_mark_row(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int r, int lane) {
     int got = 0;
-    const int rw = r >> 6;
-    const uint64_t rbit = 1ull << (r & 63);
-    for (int a = lane; a < c.R0; a += 32) {
-        if (!((c.nbm[a >> 6] >> (a & 63)) & 1ull)) continue;
-        if (a == r) {
-            for (int w = 0; w < c.W4; ++w) {
-                uint64_t bits = c.nbm[w] & c.todo[(size_t)a * c.W4 + w];
-                if (!bits) continue;
-                c.todo[(size_t)a * c.W4 + w] &= ~bits;
-                while (bits) {
-                    const int bb = w * 64 + __ffsll((long long)bits) - 1;
-                    bits &= bits - 1ull;
-                    k2w_certify(c, status, seg_base, a, bb);
+    for (int w = 0; w < c.W4; ++w) {
+        uint64_t bits = c.todo[(size_t)r * c.W4 + w] & c.nbm[w];   // uniform
+        if (!bits) continue;
+        __syncwarp();
+        if (lane == 0) c.todo[(size_t)r * c.W4 + w] &= ~bits;
+        while (bits) {
+            const int y = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1ull;
+            if (lane != (y & 31)) continue;
+            if (y >= r) {
+                // canonical bit (r, y): the candidate is open
+                if (y != r) c.todo[(size_t)y * c.W4 + (r >> 6)] &= ~(1ull << (r & 63));
+                k2w_certify(c, status, seg_base, r, y);
+                ++got;
+            } else {
+                // mirror bit: confirm with the canonical one, (y, r)
+                uint64_t* cw = c.todo + (size_t)y * c.W4 + (r >> 6);
+                const uint64_t rb = 1ull << (r & 63);
+                if (*cw & rb) {
+                    *cw &= ~rb;
+                    k2w_certify(c, status, seg_base, y, r);
                     ++got;
                 }
             }
-        } else if (c.todo[(size_t)a * c.W4 + rw] & rbit) {
-            c.todo[(size_t)a * c.W4 + rw] &= ~rbit;
-            k2w_certify(c, status, seg_base, a, r);
-            ++got;
         }
+        __syncwarp();
     }
     return got;
 }
@@ -493,7 +518,10 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     const uint8_t sb = status[q];
                     open = (sb & PPG_ST_RANK) && !(sb & PPG_ST_FEAS);
                     atomicOr(reinterpret_cast<unsigned long long*>(c.orig + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
-                    if (open) atomicOr(reinterpret_cast<unsigned long long*>(c.todo + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
+                    if (open) {
+                        atomicOr(reinterpret_cast<unsigned long long*>(c.todo + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
+                        if (a1 != b1) atomicOr(reinterpret_cast<unsigned long long*>(c.todo + (size_t)b1 * W4 + (a1 >> 6)), 1ull << (a1 & 63));
+                    }
                 }
                 int aprev = __shfl_up_sync(PPG_FULL, a1, 1);
                 if (lane == 0) {
@@ -541,7 +569,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     int na = -1;
                     for (int x = a + 1; x < R0 && na < 0; ++x)
                         for (int w = 0; w < W4; ++w)
-                            if (c.todo[(size_t)x * W4 + w]) { na = x; break; }
+                            if (c.todo[(size_t)x * W4 + w] & k2w_ge_mask(x, w)) { na = x; break; }
                     if (na < 0) break;   // segment done
                     a = na; t = a; fm = pmask;
                     if (npiv > K2W_RESET) { restart = true; continue; }   // long segment: fresh dictionary, same prefix
@@ -549,7 +577,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                 if (stage == 2) {
                     int b = -1;
                     for (int w = 0; w < W4 && b < 0; ++w) {
-                        const uint64_t x = c.todo[(size_t)a * W4 + w];
+                        const uint64_t x = c.todo[(size_t)a * W4 + w] & k2w_ge_mask(a, w);
                         if (x) b = w * 64 + __ffsll((long long)x) - 1;
                     }
                     if (b < 0) { stage = 1; continue; }
@@ -621,7 +649,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     if (!reached) {
                         ++n_give;
                         // nothing with this a can be certified by the walk
-                        if (lane == 0) for (int w = 0; w < W4; ++w) c.todo[(size_t)a * W4 + w] = 0ull;
+                        if (lane == 0) for (int w = 0; w < W4; ++w) c.todo[(size_t)a * W4 + w] &= ~k2w_ge_mask(a, w);
                         __syncwarp();
                     } else if (k_act >= 2) {
                         fm = pmask | (1ull << (~c.where[a]));
