@@ -426,7 +426,7 @@ template <class Dict>
 __global__ void __launch_bounds__(256, 1)
 k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int chunk,
-                int walker_bytes, int lds, int W4, int group_items) {
+                int walker_bytes, int lds, int W4, int group_items, int split_len) {
     extern __shared__ unsigned char k2w_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int RPL = Dict::RPL;
@@ -480,21 +480,24 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
         const long long c0 = (long long)__shfl_sync(PPG_FULL, v, 0);
         if (c0 >= n) break;
         const long long c1 = (c0 + chunk < n) ? c0 + chunk : n;
-        // a walker owns the GROUPS (prefix, second-last row) that start in [c0, c1): a group is never split, so that the
-        // certificates of one vertex reach all its candidates, while the long segments of the first prefixes (thousands
-        // of candidates with one prefix) still spread over many walkers
-        long long i = c0, own_end = c1;
-        if (c0 > 0) {
+        // Ownership.  Work items are ranges of `chunk` candidates; a range boundary x that falls inside a prefix is moved to
+        // cut(x): to the end of that prefix when less than `split` candidates of it lie beyond x (short prefixes stay whole:
+        // every certificate of a vertex reaches all candidates of its prefix), else to the next (prefix, second-last row)
+        // group (the first prefixes of a level own thousands of candidates: in one piece they would be the tail of the
+        // launch).  Both neighbours of a boundary evaluate the same function, so the pieces tile the level.
+        auto cut = [&](long long x) -> long long {
+            if (x <= 0) return 0;
+            if (x >= n) return n;
             uint64_t pfp[4]; int a_, b_;
-            split(c0 - 1, pfp, a_, b_);
-            i = seg_end(c0, n, pfp, (group_items && k_act >= 2) ? a_ : -1);
-        }
-        if (i >= c1) continue;
-        if (c1 < n) {
-            uint64_t pfp[4]; int a_, b_;
-            split(c1 - 1, pfp, a_, b_);
-            own_end = seg_end(c1, n, pfp, (group_items && k_act >= 2) ? a_ : -1);
-        }
+            split(x - 1, pfp, a_, b_);
+            const long long e = seg_end(x, n, pfp, -1);
+            if (k_act < 2 || group_items == 0) return e;
+            if (group_items == 2 || e - x >= (long long)split_len) return seg_end(x, n, pfp, a_);
+            return e;
+        };
+        const long long i0 = cut(c0), own_end = cut(c1);
+        long long i = i0;
+        if (i >= own_end) continue;
         dict.reload(P, c, lane);
         int npiv = 0, nfixed = 0;
         bool vertex_ok = true;
@@ -709,9 +712,15 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
     if (grid < 1) grid = 1;
     // ownership granularity: whole prefixes (all certificates of a vertex are used; the level is one launch and the long
     // prefixes come first in lexicographic order, so the dynamic queue schedules longest-first) or (prefix, row) groups
-    static const int group_items = getenv("PPGPU_K2W_GROUPS") ? atoi(getenv("PPGPU_K2W_GROUPS")) : 0;
+    // PPGPU_K2W_GROUPS: 0 whole prefixes only, 1 long prefixes are cut at group boundaries, 2 always cut at groups.
+    // Default: whole prefixes while every walker has plenty of work (1 GPU, level 5 of the bench program: 60 k candidates
+    // per walker; measured 236 ms whole / 243 ms cut at 2048 / 256 ms cut at 1024), cut the long ones when a walker's share
+    // is small and one 6 k-candidate prefix would be the tail of the launch (a level sharded over 8 GPUs, level 4)
+    static const int groups_env = getenv("PPGPU_K2W_GROUPS") ? atoi(getenv("PPGPU_K2W_GROUPS")) : -1;
+    static const int split_len = getenv("PPGPU_K2W_SPLIT") ? atoi(getenv("PPGPU_K2W_SPLIT")) : 2048;
+    const int group_items = groups_env >= 0 ? groups_env : (n / walkers < 16384 ? 1 : 0);
     kern<<<(unsigned)grid, 32 * wpc, smem, st>>>(P, masks, n, k_act, status, queue, counters, (int)chunk, (int)wb, lds, W4,
-                                                 group_items);
+                                                 group_items, split_len);
     *handled = true;
     return cudaGetLastError();
 }
