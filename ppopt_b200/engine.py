@@ -448,7 +448,10 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         t0 = time.perf_counter()
         k_act = lvl + 1
         status = _eval_level(eng, masks, k_act, dist, rank, world)
-        if bool(((status & ST_NUMERIC) != 0).any().item()):
+        # one device reduction answers "is any candidate flagged at all" for the three report bits (a sync per question
+        # is what the small levels and the sharded runs pay for)
+        any_flag = int((status & (ST_NUMERIC | ST_THIN | ST_BORDER)).max().item()) if n else 0
+        if any_flag & ST_NUMERIC:
             _escalate_numeric(eng, masks, status, k_act, flagged, lvl + 1)
         n_reg = 0
         opt_idx = eng.select(status, ST_OPT, ST_OPT)
@@ -485,16 +488,24 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
                     built = build_regions(eng, cr_cls, asets, k_act, laws, rows, flags, info, d2h=copied)
                     eng.d2h_bytes += sum(copied)
                     regions.extend(r for r in built if r is not None)
-            n_reg = int(((status & ST_REGION) != 0).sum().item())
-        feas_idx = eng.select(status, ST_FEAS, ST_FEAS)
-        n_feas = int(feas_idx.shape[0])
-        if bool(((status & (ST_THIN | ST_BORDER)) != 0).any().item()):
+            # (K5 decides full dimension with the accurate radius and may raise the THIN bit itself)
+            after = torch.stack([((status & ST_REGION) != 0).sum(), (status & (ST_THIN | ST_BORDER)).max().to(torch.int64)]).cpu()
+            n_reg = int(after[0])
+            any_flag |= int(after[1])
+        last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
+        if last:
+            # no next level: only the count is needed, not the ordered index list
+            feas_idx = None
+            n_feas = int(((status & ST_FEAS) != 0).sum().item())
+        else:
+            feas_idx = eng.select(status, ST_FEAS, ST_FEAS)
+            n_feas = int(feas_idx.shape[0])
+        if any_flag & (ST_THIN | ST_BORDER):
             _collect_flags(eng, masks, status, flagged)
         if collect_status:
             statuses.append((masks.cpu().numpy(), status.cpu().numpy()))
         if digest:
             sums.append((n, _checksum(status)))
-        last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
         nxt = eng.children(masks, feas_idx, k_act, dist if world > 1 else None) if not last else eng.empty((0, eng.W), torch.int64)
         torch.cuda.synchronize(eng.tdev)
         total += n

@@ -10,11 +10,12 @@ evaluates its chunks in place in a full-length status vector that is zero elsewh
 vector then gives every rank all statuses, after which each rank regenerates the identical next level (K6 is
 deterministic and replicated).  No numerical data is ever reduced.
 """
+import os
 from typing import List, Tuple
 
 import torch
 
-CHUNKS_PER_RANK = 16
+CHUNKS_PER_RANK = int(os.environ.get('PPGPU_CHUNKS_PER_RANK', '16'))
 MIN_CHUNK = 65536
 
 
