@@ -730,6 +730,162 @@ K2aOut k2p_certify(const ReducedProgram& P, const std::vector<int>& act, int max
     return out;
 }
 
+// ---- K2w: sequential statement of k2w_walk_kernel (ppopt_b200/csrc/k2w_walk.cu) -------------------------------------------
+// One walker processes the candidates of a level in order, prefix by prefix (a prefix = all active rows but the last two),
+// exactly like a device walker processes one work item: slack dictionary s_B = beta - D s_N reloaded from the host-built
+// vertex, drive(row) by primal simplex pivots (largest positive coefficient of the target row enters, Harris ratio test,
+// the target row wins when eligible), prefix rows fixed first, then for every second-last row a: drive a, fix it, drive
+// every still-open b; after every pivot all open candidates whose last two rows are nonbasic are certified.  Same
+// constants as the kernel (pivot floor 1e-7, certification band 1e-8, 400 pivots per drive, reload after 3000 pivots).
+struct WalkDict {
+    int nb, nf, ld;
+    std::vector<double> D;        // nb x ld  [beta | coefficients]
+    std::vector<int> bvar, nvar, where;
+    long pivots = 0;
+    bool ok = true;               // every basic slack >= -1e-8 after the last pivot
+    void load(const ReducedProgram& P) {
+        nb = P.wk_nb; nf = P.nfree; ld = P.wk_ld;
+        D = P.wk_D0; bvar = P.wk_bvar; nvar = P.wk_nvar;
+        where.assign(P.R0, 0);
+        for (int i = 0; i < nb; ++i) where[bvar[i]] = i;
+        for (int j = 0; j < nf; ++j) where[nvar[j]] = ~j;
+        ok = true;
+    }
+    bool nonbasic(int r) const { return where[r] < 0; }
+    void pivot(int l, int j) {
+        const int cj = 1 + j;
+        const double inv = 1.0 / D[(size_t)l * ld + cj];
+        std::vector<double> q(ld);
+        for (int k = 0; k < ld; ++k) q[k] = k == cj ? 0.0 : D[(size_t)l * ld + k] * inv;
+        ok = true;
+        for (int r = 0; r < nb; ++r) {
+            if (r == l) continue;
+            const double col = D[(size_t)r * ld + cj];
+            if (col != 0.0) {
+                for (int k = 0; k < ld; ++k) D[(size_t)r * ld + k] = std::fma(-col, q[k], D[(size_t)r * ld + k]);
+                D[(size_t)r * ld + cj] = -col * inv;
+            }
+            if (!(D[(size_t)r * ld] >= -1e-8)) ok = false;
+        }
+        for (int k = 0; k < ld; ++k) D[(size_t)l * ld + k] = k == cj ? inv : q[k];
+        const int rl = bvar[l], rn = nvar[j];
+        bvar[l] = rn; nvar[j] = rl; where[rn] = l; where[rl] = ~j;
+        ++pivots;
+    }
+    // returns the row that became nonbasic by the pivot (or -1 when no pivot was possible), reached = target is nonbasic
+    template <class OnPivot>
+    bool drive(int t, const std::vector<char>& fixed_col, OnPivot&& on_pivot) {
+        for (int it = 0; it < 400; ++it) {
+            const int wi = where[t];
+            if (wi < 0) return true;
+            const double bi = D[(size_t)wi * ld];
+            const bool degen = bi <= 1e-11;
+            double best = 0.0; int j = -1;
+            for (int jj = 0; jj < nf; ++jj) {
+                if (fixed_col[jj]) continue;
+                double x = D[(size_t)wi * ld + 1 + jj];
+                if (degen) x = std::fabs(x);
+                if (x > best) { best = x; j = jj; }
+            }
+            if (!(best > 1e-7)) return false;
+            int l = wi;
+            if (!degen) {
+                double hb = INFINITY;
+                for (int r = 0; r < nb; ++r) {
+                    const double a = D[(size_t)r * ld + 1 + j];
+                    if (a > PPG_TINY) hb = std::fmin(hb, (std::fmax(D[(size_t)r * ld], 0.0) + PPG_HARRIS) / a);
+                }
+                const double at = D[(size_t)wi * ld + 1 + j];
+                if (!(std::fmax(bi, 0.0) / at <= hb)) {
+                    double lp = 0.0; l = -1;
+                    for (int r = 0; r < nb; ++r) {
+                        const double a = D[(size_t)r * ld + 1 + j];
+                        if (a > PPG_TINY && std::fmax(D[(size_t)r * ld], 0.0) / a <= hb && a > lp) { lp = a; l = r; }
+                    }
+                    if (l < 0) return false;
+                }
+            }
+            const int rl = bvar[l];
+            pivot(l, j);
+            if (!ok) return false;
+            on_pivot(rl);
+        }
+        return false;
+    }
+};
+
+// certified[i] = 1 for every candidate the walk certifies; returns the number of pivots
+long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std::vector<char>& certified) {
+    certified.assign(n, 0);
+    if (!P.wk_ok || n == 0) return 0;
+    std::vector<std::vector<int>> acts(n);
+    for (long i = 0; i < n; ++i) active_list(P, masks + i * P.W, acts[i]);
+    const int k = (int)acts[0].size();
+    if (k < 1) return 0;
+    const int p = k >= 2 ? k - 2 : 0;
+    WalkDict wd;
+    wd.load(P);
+    long total = 0;
+    std::vector<int> fixed_rows;
+    long i = 0;
+    while (i < n) {
+        long s1 = i + 1;
+        while (s1 < n && std::equal(acts[i].begin(), acts[i].begin() + p, acts[s1].begin())) ++s1;
+        // open candidates of the segment: (a, b) -> index
+        std::vector<std::vector<long>> open(P.R0, std::vector<long>(P.R0, -1));
+        for (long q = i; q < s1; ++q) {
+            const int b = acts[q][k - 1], a = k >= 2 ? acts[q][k - 2] : b;
+            open[a][b] = q;
+        }
+        auto mark_row = [&](int r) {
+            for (int y = 0; y < P.R0; ++y) {
+                if (!wd.nonbasic(y)) continue;
+                const int a = std::min(r, y), b = std::max(r, y);
+                if (open[a][b] >= 0) { certified[open[a][b]] = 1; open[a][b] = -1; }
+            }
+        };
+        bool restart = wd.pivots > 3000 || !wd.ok;
+        auto fix_prefix = [&]() -> bool {
+            if (restart) { total += wd.pivots; wd.pivots = 0; wd.load(P); fixed_rows.clear(); restart = false; }
+            size_t keep = 0;
+            while (keep < fixed_rows.size() && keep < (size_t)p && fixed_rows[keep] == acts[i][keep]) ++keep;
+            fixed_rows.resize(keep);
+            for (int f = (int)keep; f < p; ++f) {
+                std::vector<char> fc(wd.nf, 0);
+                for (int r : fixed_rows) fc[~wd.where[r]] = 1;
+                if (!wd.drive(acts[i][f], fc, [](int) {})) return false;
+                fixed_rows.push_back(acts[i][f]);
+            }
+            return true;
+        };
+        if (fix_prefix()) {
+            for (int r = 0; r < P.R0; ++r) if (wd.nonbasic(r)) mark_row(r);
+            for (int a = 0; a < P.R0 && wd.ok; ++a) {
+                bool any = false;
+                for (int b = a; b < P.R0; ++b) any = any || open[a][b] >= 0;
+                if (!any) continue;
+                if (wd.pivots > 3000) {
+                    restart = true;
+                    if (!fix_prefix()) break;
+                    for (int r = 0; r < P.R0; ++r) if (wd.nonbasic(r)) mark_row(r);
+                }
+                std::vector<char> fc(wd.nf, 0);
+                for (int r : fixed_rows) fc[~wd.where[r]] = 1;
+                if (!wd.drive(a, fc, mark_row)) { for (int b = a; b < P.R0; ++b) open[a][b] = -1; continue; }
+                if (k < 2) continue;
+                fc[~wd.where[a]] = 1;
+                for (int b = a + 1; b < P.R0 && wd.ok; ++b) {
+                    if (open[a][b] < 0) continue;
+                    wd.drive(b, fc, mark_row);
+                    open[a][b] = -1;   // certified by the marking, or left to the relaxation
+                }
+            }
+        }
+        i = s1;
+    }
+    return total + wd.pivots;
+}
+
 }  // namespace
 
 extern "C" {
@@ -819,6 +975,13 @@ int twin_walk_dict(void* h, int* nb, int* ld, double* D0, int* bvar, int* nvar) 
     if (bvar) std::memcpy(bvar, P.wk_bvar.data(), P.wk_bvar.size() * sizeof(int));
     if (nvar) std::memcpy(nvar, P.wk_nvar.data(), P.wk_nvar.size() * sizeof(int));
     return 1;
+}
+// K2w on one level (candidates in lexicographic order): certified flags, returns the number of pivots
+long twin_k2w(void* h, const uint64_t* masks, long ncand, uint8_t* certified) {
+    std::vector<char> c;
+    const long piv = k2w_walk_level(((Twin*)h)->P, masks, ncand, c);
+    for (long i = 0; i < ncand; ++i) certified[i] = (uint8_t)c[i];
+    return piv;
 }
 int twin_rows(void* h) { return ((Twin*)h)->P.R0; }
 int twin_nfree(void* h) { return ((Twin*)h)->P.nfree; }

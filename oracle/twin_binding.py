@@ -126,6 +126,16 @@ class Twin:
         l.twin_t0(self.h, T0.ctypes.data)
         return D0, bvar, nvar, T0
 
+    def k2w(self, masks):
+        """sequential K2w (vertex walk) over one level in lexicographic order: (certified flags, pivots)"""
+        l = lib()
+        l.twin_k2w.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+        l.twin_k2w.restype = ctypes.c_long
+        masks = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(-1, self.W)
+        cert = numpy.zeros(masks.shape[0], dtype=numpy.uint8)
+        piv = l.twin_k2w(self.h, masks.ctypes.data, masks.shape[0], cert.ctypes.data)
+        return cert, int(piv)
+
     def pivots(self):
         return lib().twin_pivots(self.h)
 

@@ -99,3 +99,32 @@ def test_walk_start_vertex_is_a_feasible_vertex(name):
     assert numpy.max(numpy.abs(D0[:, 1:] + M[bvar])) <= 1e-9 * max(1.0, float(numpy.max(numpy.abs(M))))
     assert numpy.max(numpy.abs(D0[:, 0] - numpy.maximum(beta, 0.0))) <= 1e-9 * scale
     assert beta.min() >= -1e-9 * scale
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_walk_certificates_are_sound(name):
+    """CPU restatement of K2w (oracle/twin.cpp::k2w_walk_level = csrc/k2w_walk.cu): on every golden level no candidate the
+    walk certifies is infeasible for the unmodified reference, and on programs whose feasible sets dominate it certifies
+    most of them with about one pivot per candidate"""
+    from twin_binding import Twin
+    path = os.path.join(GOLDEN, name + '.npz')
+    g = numpy.load(path)
+    tw = Twin.from_npz(path)
+    if tw.walk_dict() is None:
+        pytest.skip('no start vertex')
+    tot = cert = feas = piv = 0
+    n_eq = int(g['n_eq'])
+    for lv in range(int(g['n_levels'])):
+        c, st = g[f'level{lv}_candidates'], g[f'level{lv}_status']
+        if len(c) == 0 or c.shape[1] - n_eq > 32 or len(c) > 200000:
+            continue          # (whole levels, in order: the walk shares certificates between neighbours)
+        cert_f, p = tw.k2w(tw.masks(c.tolist()))
+        ok = (st & 3) == 3          # full rank and feasible for the reference
+        # (the kernel only looks at candidates that passed the rank screen: the LP of a rank-deficient set may well be
+        # feasible, the reference reports such sets infeasible without solving it, mplp_program.py:433-435)
+        bad = cert_f.astype(bool) & ((st & 1) != 0) & ((st & 2) == 0)
+        assert not numpy.any(bad), f'{name}: the walk certified an infeasible candidate'
+        tot += len(c); cert += int(numpy.sum(cert_f.astype(bool) & ok)); feas += int(ok.sum()); piv += p
+    assert tot > 0
+    if name == 'synthetic_30_6_40_s0':
+        assert cert >= 0.99 * feas and piv <= 2.0 * tot, (cert, feas, piv, tot)
