@@ -9,15 +9,15 @@ Workload (config.workload): BASELINE.json configs[4], the synthetic dense mpQP w
 combinatorial levels 1..L (default L = 5: 74,536,536 candidate active sets; L = 4: 3,940,375; L = 3: 163,810).
 A "step" is one full pass of the level loop over that program.
 
-  value   device-resident throughput: program constants already in HBM, every kernel of the path runs (K1 rank, K2a/K2
-          feasibility, K3/K4 optimality screen, K5 region emission, K6 next-level generation), region buffers stay
+  value   device-resident throughput: program constants already in HBM, every kernel of the path runs (K1 rank, K2w / K2a /
+          K2 feasibility, K3/K4 optimality screen, K5 region emission, K6 next-level generation), region buffers stay
           in HBM.  CUDA events on the launch stream, max over ranks, L2 flushed between steps.
   e2e     the same pass through the public call solve_mpqp(program, mpqp_algorithm.combinatorial) with HOST numpy
           program data: upload, all kernels, download of the region matrices, CriticalRegion objects built.
-  roofline  the kernel family with the largest share of the step: useful fp64 flops counted in-kernel / its summed launch
-          durations (CUDA events recorded around each launch inside libppgpu), against the fp64 FMA peak measured on this
-          device by a register-resident DFMA loop (MEASURED_PEAKS.json has no fp64 entry).  The path is fp64 / issue-
-          latency bound, not HBM bound: 8W+2 algorithmic bytes per candidate.
+  roofline  the kernel family with the largest share of the step (round 2: the vertex walk K2w): useful fp64 flops counted
+          in-kernel / its summed launch durations (CUDA events recorded around each launch inside libppgpu), against the
+          fp64 FMA peak measured on this device by a register-resident DFMA loop (MEASURED_PEAKS.json has no fp64 entry).
+          The path is fp64 / shared-memory-latency bound, not HBM bound: 8W+2 algorithmic bytes per candidate per pass.
   parity  N > 1: the sharded run's digest (decision bits of every candidate of every level + the region list) must
           equal the digest of a single-GPU run of the same program made by rank 0 in the same process; the bench FAILS
           otherwise.

@@ -707,7 +707,9 @@ K2aOut k2p_certify(const ReducedProgram& P, const std::vector<int>& act, int max
             exact();
             double worst = 0.0;
             for (int r = 0; r < R0; ++r) worst = std::fmax(worst, park[r] ? std::fabs(s[r]) : s[r]);
-            if (mode == 1 && worst <= PPG_FEAS_TOL) { feasible = true; break; }
+            double eqm = 0.0, sm = 1.0;
+            for (int r = 0; r < R0; ++r) { sm = std::fmax(sm, std::fabs(s[r])); if (park[r]) eqm = std::fmax(eqm, std::fabs(s[r])); }
+            if (mode == 1 && worst <= PPG_FEAS_TOL && eqm <= 1e-9 * sm) { feasible = true; break; }
             if (mode == 1 && rechecks < 3) {
                 ++rechecks;
                 for (int r = 0; r < R0; ++r) v[r] = park[r] ? -1e300 : s[r];

@@ -473,11 +473,11 @@ k2p_relax_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, 
                         fin = __all_sync(PPG_FULL, fin);
                         // hand-over only from a point whose residual vector is trustworthy (see oracle/twin.cpp k2p_certify):
                         // noise on the active rows = noise on every row; such candidates go to the simplex cold
-                        if (omode == 2 || worst > PPG_FEAS_TOL) {
-                            eqmax = warp_max_nonneg(eqmax);
-                            smax = warp_max_nonneg(smax);
-                            fin = fin && eqmax <= 1e-9 * smax;
-                        }
+                        // the active rows must hold as EQUALITIES, not merely within the LP tolerance (the simplex pivots them
+                        // out exactly): a certificate, like a hand-over point, needs their residuals at rounding level
+                        eqmax = warp_max_nonneg(eqmax);
+                        smax = warp_max_nonneg(smax);
+                        fin = fin && eqmax <= 1e-9 * smax;
                         const bool pass = omode == 1 && worst <= PPG_FEAS_TOL && fin;
                         bool again = false;
                         if (!pass && omode == 1) {
