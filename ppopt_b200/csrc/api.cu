@@ -253,10 +253,16 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
     cudaError_t e;
     if (stages & 1) {
         ProfScope ps(p, st, 0);
-        e = launch_k1(p->dev, d_masks, n, k_act, d_status, p->d_counters, p->sm_count, st);
-        if (e != cudaSuccess) return fail("K1 rank", e);
-        if (k_act >= 1 && k_act <= 8) p->launches++;  // prefilter + QR
-        p->launches++;
+        // K1 is two passes over the same bytes (thread-per-candidate prefilter, then QR of what it could not clear): in
+        // pieces of 2^22 candidates the second pass finds masks and status in L2 (one 70 M-candidate launch: 9.8 vs 7.0 ms)
+        const long long piece = 1ll << 22;
+        for (long long off = 0; off < n; off += piece) {
+            const long long nn = n - off < piece ? n - off : piece;
+            e = launch_k1(p->dev, d_masks + (size_t)off * p->dev.W, nn, k_act, d_status + off, p->d_counters, p->sm_count, st);
+            if (e != cudaSuccess) return fail("K1 rank", e);
+            if (k_act >= 1 && k_act <= 8) p->launches++;  // prefilter + QR
+            p->launches++;
+        }
     }
     static const int warm_on = getenv("PPGPU_WARM") ? atoi(getenv("PPGPU_WARM")) : 1;
     p->dev.warm_count = nullptr; p->dev.warm_resid = nullptr; p->dev.warm_idx = nullptr; p->dev.warm_cap = 0;
