@@ -262,6 +262,7 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
             if (e != cudaSuccess) return fail("K1 rank", e);
             if (k_act >= 1 && k_act <= 8) p->launches++;  // prefilter + QR
             p->launches++;
+            if (k_act >= 2 && k_act <= p->dev.np) p->launches++;   // singular-value re-check of borderline decisions
         }
     }
     static const int warm_on = getenv("PPGPU_WARM") ? atoi(getenv("PPGPU_WARM")) : 1;

@@ -277,13 +277,111 @@ static cudaError_t launch_k1_np(const DevProgram& P, const uint64_t* masks, long
     return launch_k1_t<NP, 1>(P, masks, n, k_act, status, counters, sm_count, st);
 }
 
+// Borderline escalation: candidates whose pivoted-QR ratio fell inside the borderline band are
+// decided again the way the reference decides - by singular values: numpy.linalg.matrix_rank counts the singular values
+// above sigma_max * max(M, N) * eps (constraint_utilities.py:236).  One warp per flagged candidate, one-sided Jacobi
+// (Hestenes) on the k' x np matrix of reduced rows in shared memory: rows are rotated pairwise until mutually orthogonal,
+// their norms are the singular values (small ones to high RELATIVE accuracy, which is what a rank decision at 1e-15 needs).
+// Every warp scans the status bytes of the launch for PPG_ST_BORDER (70 MB at the largest level: microseconds), so no host
+// round trip is needed between the QR and the feasibility stage.  The flag stays set: the decision is reported either way.
+__global__ void __launch_bounds__(128)
+k1_svd_recheck_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
+                      int warp_doubles) {
+    extern __shared__ double k1s_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* M = k1s_smem + (size_t)warp * warp_doubles;   // k x np
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const int W = P.W, np = P.np;
+    for (long long base = gw * 32; base < n; base += nw * 32) {
+        const long long mine = base + lane;
+        const uint8_t sb = mine < n ? status[mine] : 0;
+        unsigned todo = __ballot_sync(PPG_FULL, (sb & PPG_ST_BORDER) != 0);
+        while (todo) {
+            const int src = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const long long idx = base + src;
+            const uint64_t* mk = masks + idx * W;
+            const int k = k_act >= 0 ? k_act : mask_popc(mk, W);
+            __syncwarp();
+            for (int e = lane; e < k * np; e += 32) {
+                const int r = e / np, c = e - r * np;
+                M[e] = __ldg(P.At + (size_t)mask_nth(mk, W, r) * np + c);
+            }
+            __syncwarp();
+            for (int sweep = 0; sweep < 40; ++sweep) {
+                bool rotated = false;
+                for (int p = 0; p < k - 1; ++p)
+                    for (int q = p + 1; q < k; ++q) {
+                        double a = 0.0, b = 0.0, g = 0.0;
+                        for (int c = lane; c < np; c += 32) {
+                            const double x = M[p * np + c], y = M[q * np + c];
+                            a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) { a += shfl_xor_d(a, o); b += shfl_xor_d(b, o); g += shfl_xor_d(g, o); }
+                        if (fabs(g) > 1e-15 * sqrt(a * b) && g != 0.0) {
+                            rotated = true;
+                            const double zeta = (b - a) / (2.0 * g);
+                            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                            const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                            for (int c = lane; c < np; c += 32) {
+                                const double x = M[p * np + c], y = M[q * np + c];
+                                M[p * np + c] = cs * x - sn * y;
+                                M[q * np + c] = sn * x + cs * y;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                if (!rotated) break;
+            }
+            double smax = 0.0, smin = CUDART_INF;
+            for (int r = 0; r < k; ++r) {
+                double a = 0.0;
+                for (int c = lane; c < np; c += 32) a = fma(M[r * np + c], M[r * np + c], a);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += shfl_xor_d(a, o);
+                const double sg = sqrt(a);
+                smax = fmax(smax, sg); smin = fmin(smin, sg);
+            }
+            // matrix_rank's tolerance, with the dimensions of the matrix the reference looks at (all active rows x n)
+            const int Mr = P.ne + k, Nc = P.n;
+            const double tol = smax * (double)(Mr > Nc ? Mr : Nc) * 2.220446049250313e-16;
+            const bool full = k <= np && smin > tol;
+            if (lane == 0) {
+                const uint8_t st = status[idx];
+                status[idx] = full ? (uint8_t)(st | PPG_ST_RANK) : (uint8_t)(st & ~PPG_ST_RANK);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static cudaError_t launch_k1_svd(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
+                                 int sm_count, cudaStream_t st) {
+    const int kmax = k_act >= 0 ? k_act : P.mi;
+    if (kmax < 2 || kmax > P.np) return cudaSuccess;   // one row is never borderline; more rows than columns: deficient by counting
+    const int wd = kmax * P.np;
+    const size_t smem = (size_t)4 * wd * sizeof(double);
+    if (smem > 200 * 1024) return cudaSuccess;
+    if (smem > 48 * 1024) {
+        cudaError_t e = allow_max_smem(k1_svd_recheck_kernel);
+        if (e != cudaSuccess) return e;
+    }
+    long long grid = (n + 127) / 128;
+    if (grid > (long long)sm_count * 4) grid = (long long)sm_count * 4;
+    k1_svd_recheck_kernel<<<(unsigned)grid, 128, smem, st>>>(P, masks, n, k_act, status, wd);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_k1(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                       unsigned long long* counters, int sm_count, cudaStream_t st) {
-    if (P.np <= 8) return launch_k1_np<8>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (P.np <= 16) return launch_k1_np<16>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (P.np <= 32) return launch_k1_np<32>(P, masks, n, k_act, status, counters, sm_count, st);
-    if (P.np <= 64) return launch_k1_t<64, 2>(P, masks, n, k_act, status, counters, sm_count, st);
-    return cudaErrorInvalidValue;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (P.np <= 8) e = launch_k1_np<8>(P, masks, n, k_act, status, counters, sm_count, st);
+    else if (P.np <= 16) e = launch_k1_np<16>(P, masks, n, k_act, status, counters, sm_count, st);
+    else if (P.np <= 32) e = launch_k1_np<32>(P, masks, n, k_act, status, counters, sm_count, st);
+    else if (P.np <= 64) e = launch_k1_t<64, 2>(P, masks, n, k_act, status, counters, sm_count, st);
+    if (e != cudaSuccess) return e;
+    return launch_k1_svd(P, masks, n, k_act, status, sm_count, st);
 }
 
 }  // namespace ppgpu

@@ -37,7 +37,7 @@
 // column-pivoted QR: rank deficient iff |R_kk| <= PPG_RANK_TOL * |R_11|
 // (numpy.linalg.matrix_rank default: sigma_min <= sigma_max * max(k,n) * eps, constraint_utilities.py:236)
 #define PPG_RANK_TOL 1e-11
-#define PPG_RANK_BORDER_LO 1e-13
+#define PPG_RANK_BORDER_LO 1e-15   // below: exactly dependent rows (3e-16 on the MPC programs); above: re-decided by singular values
 #define PPG_RANK_BORDER_HI 1e-7
 
 // per-candidate status byte (bits 0-3 match tests/golden level*_status)
