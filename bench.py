@@ -422,9 +422,20 @@ def run_gpu(args, rank, world, local_rank):
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
-    traffic = None
+    traffic, smem = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', f'r02_{dom}_traffic.json'))).get('dram_bytes_per_launch')
+        tj = json.load(open(os.path.join(ROOT, 'profiles', f'r02_{dom}_traffic.json')))
+        traffic = tj.get('dram_bytes_per_launch')
+        if dom == 'k2w_walk':
+            # what actually bounds the walk: every entry of the slack dictionary is read and written once per pivot in SHARED
+            # memory (16 B per counted FMA); peak = 128 B / clock / SM at the SM clock sampled during the timed region
+            clk = (sampler.summary().get('sm_mhz') or 1965.0) * 1e6
+            sm_peak = eng.sm_count * 128.0 * clk / 1e12
+            sm_ach = 16.0 * dom_work / max(k2['ms'] * 1e-3, 1e-12) / 1e12
+            smem = {'bound': 'shared memory', 'achieved': sm_ach, 'peak': sm_peak, 'unit': 'TB/s', 'frac': sm_ach / sm_peak,
+                    'ncu_wavefronts_pct_of_peak': tj.get('smem_wavefronts_pct_of_peak'),
+                    'note': 'algorithmic shared-memory bytes (dictionary read + write per pivot) over the kernel time; the ncu figure '
+                            'counts every shared-memory wavefront of the level-5 launch (profiles/r02_k2w_ncu.txt)'}
     except Exception:
         pass
     line = {
@@ -451,6 +462,7 @@ def run_gpu(args, rank, world, local_rank):
                      'flop_model': 'useful fp64 FMAs counted in-kernel: K2w pivots x basic rows x columns of the slack dictionary '
                                    '(rank-1 update); K2a relaxation steps x R0 x 3; K2/K4 pivots x live rows x columns',
                      'k2w': {'certified': counters['k2w_certified'], 'pivots': counters['k2w_pivots'], 'gave_up': counters['k2w_giveup']},
+                     'shared_memory': smem,
                      'k2a': {'tried': counters['k2a_tried'], 'certified': counters['k2a_certified'], 'steps': counters['k2a_steps']},
                      'k2': {'lps': counters['k2_lps'], 'pivots': counters['k2_pivots']},
                      'hbm': {'achieved': hbm_bytes / max(k2['ms'] * 1e-3, 1e-12) / 1e9, 'peak': peaks.get('hbm_gbs'),
