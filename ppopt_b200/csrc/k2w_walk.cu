@@ -117,6 +117,7 @@ template <int RPL_, int LD_ = 0>
 struct K2wSmemDict {
     static constexpr int RPL = RPL_;
     static constexpr bool IN_SMEM = true;
+    static constexpr int SMEM_ROW0 = 0;
     __device__ __forceinline__ void reload(const DevProgram& P, const K2wCtx& c, int lane) {
         for (int e = lane; e < c.nb * c.ld; e += 32) {
             const int r = e / c.ld, k = e - r * c.ld;
@@ -240,6 +241,148 @@ struct K2wSmemDict {
     }
 };
 
+// ---- storage policy C: HYBRID - the first 32 basic rows (row slot 0: one row per lane) in REGISTERS, the other slots in
+// shared memory.  The walk is bound by shared-memory bandwidth (a pivot reads and writes every dictionary entry: ncu 69 %
+// of the wavefront peak with everything in shared memory); one slot in registers removes 4 of the 11 wavefronts per column
+// of the rank-1 update while the register count stays where it is (LD doubles more per thread: no spills, unlike the
+// all-register policy B).  LD = wk_ld exactly (compile-time, odd).  Register arrays are only indexed by constants
+// (static_for / reg_pick / reg_set).
+template <int RPL_, int LD>
+struct K2wHybridDict {
+    static constexpr int RPL = RPL_;
+    static constexpr bool IN_SMEM = true;
+    static constexpr int SMEM_ROW0 = 32;   // shared memory holds rows 32.. (row r at (r - 32) * LD)
+    double T0[LD];                          // row `lane` of the dictionary
+    __device__ __forceinline__ void reload(const DevProgram& P, const K2wCtx& c, int lane) {
+#pragma unroll
+        for (int k = 0; k < LD; ++k) T0[k] = lane < c.nb ? __ldg(P.wk_D0 + (size_t)lane * LD + k) : 0.0;
+        for (int e = lane + 32 * LD; e < c.nb * LD; e += 32) c.D[e - 32 * LD] = __ldg(P.wk_D0 + e);
+        k2w_reload_labels(P, c, lane);
+    }
+    __device__ __forceinline__ void target_scan(const K2wCtx& c, int wi, uint64_t fm, int lane, double& bi, double& wbest, int& j) {
+        if (wi < 32) {
+            // the owner lane scans its own registers, the result is broadcast
+            const double b0 = T0[0];
+            const bool degen = b0 <= 1e-11;
+            double best = 0.0; int bj = 0x7fffffff;
+#pragma unroll
+            for (int k = 1; k < LD; ++k) {
+                double x = T0[k];
+                if (degen) x = fabs(x);
+                if (!((fm >> (k - 1)) & 1ull) && x > best) { best = x; bj = k - 1; }
+            }
+            bi = shfl_d(b0, wi);
+            wbest = shfl_d(best, wi);
+            j = __shfl_sync(PPG_FULL, bj, wi);
+        } else {
+            const double* Di = c.D + (size_t)(wi - 32) * LD;
+            bi = Di[0];
+            const bool degen = bi <= 1e-11;
+            double best = 0.0; int bj = 0x7fffffff;
+            for (int jj = lane; jj < c.nf; jj += 32) {
+                if ((fm >> jj) & 1ull) continue;
+                double x = Di[1 + jj];
+                if (degen) x = fabs(x);
+                if (x > best) { best = x; bj = jj; }
+            }
+            wbest = warp_max_nonneg(best);
+            j = __reduce_min_sync(PPG_FULL, best == wbest ? bj : 0x7fffffff);
+        }
+    }
+    __device__ __forceinline__ void column(const K2wCtx& c, int j, int lane, double (&col)[RPL], double (&beta)[RPL]) {
+        col[0] = lane < c.nb ? reg_pick<LD>(T0, 1 + j) : 0.0;
+        beta[0] = T0[0];
+#pragma unroll
+        for (int rr = 1; rr < RPL; ++rr) {
+            const int r = lane + 32 * rr;
+            col[rr] = r < c.nb ? c.D[(size_t)(r - 32) * LD + 1 + j] : 0.0;
+            beta[rr] = r < c.nb ? c.D[(size_t)(r - 32) * LD] : 0.0;
+        }
+    }
+    __device__ __forceinline__ bool pivot(const K2wCtx& c, int l, int j, int lane) {
+        const int cj = 1 + j, nb = c.nb;
+        const bool l_in_regs = l < 32;
+        double* Dl = c.D + (size_t)(l_in_regs ? 0 : l - 32) * LD;
+        const double c0 = reg_pick<LD>(T0, cj);       // my register row's entry in the entering column
+        const double piv = l_in_regs ? shfl_d(c0, l) : Dl[cj];
+        const double inv = k2w_rcp(piv);
+        __syncwarp();
+        if (l_in_regs) {
+            if (lane == l) {
+#pragma unroll
+                for (int k = 0; k < LD; ++k) c.prow[k] = T0[k] * inv;
+                c.prow[cj] = 0.0;
+            }
+        } else {
+            for (int k = lane; k < LD; k += 32) c.prow[k] = (k == cj) ? 0.0 : Dl[k] * inv;
+        }
+        __syncwarp();
+        double colr[RPL];
+        double* Dr[RPL];
+        colr[0] = (lane < nb && lane != l) ? c0 : 0.0;
+        Dr[0] = nullptr;
+#pragma unroll
+        for (int rr = 1; rr < RPL; ++rr) {
+            const int r = lane + 32 * rr;
+            Dr[rr] = c.D + (size_t)(r < nb ? r - 32 : 0) * LD;
+            colr[rr] = (r < nb && r != l) ? Dr[rr][cj] : 0.0;
+        }
+        const double* __restrict__ q = c.prow;
+        const bool own = l_in_regs && lane == l;
+        constexpr int G = 8;
+        bool okb = true;
+        static_for<(LD + G - 1) / G>([&](auto KK) {
+            constexpr int k0 = decltype(KK)::value * G;
+            constexpr int GN = (LD - k0) < G ? (LD - k0) : G;
+            double qk[GN], x[RPL][GN];
+#pragma unroll
+            for (int g = 0; g < GN; ++g) qk[g] = q[k0 + g];
+#pragma unroll
+            for (int rr = 1; rr < RPL; ++rr)
+#pragma unroll
+                for (int g = 0; g < GN; ++g) x[rr][g] = Dr[rr][k0 + g];
+            // slot 0: registers; the pivot row's owner takes the scaled row itself
+#pragma unroll
+            for (int g = 0; g < GN; ++g) {
+                const double v = fma(-colr[0], qk[g], T0[k0 + g]);
+                T0[k0 + g] = own ? qk[g] : v;
+            }
+#pragma unroll
+            for (int rr = 1; rr < RPL; ++rr)
+#pragma unroll
+                for (int g = 0; g < GN; ++g) x[rr][g] = fma(-colr[rr], qk[g], x[rr][g]);
+            if constexpr (k0 == 0) {
+                okb = okb && (lane >= nb || lane == l || T0[0] >= -K2W_NEG_OK);
+#pragma unroll
+                for (int rr = 1; rr < RPL; ++rr) {
+                    const int r = lane + 32 * rr;
+                    okb = okb && (r >= nb || r == l || x[rr][0] >= -K2W_NEG_OK);
+                }
+            }
+#pragma unroll
+            for (int rr = 1; rr < RPL; ++rr)
+                if (colr[rr] != 0.0) {
+#pragma unroll
+                    for (int g = 0; g < GN; ++g) Dr[rr][k0 + g] = x[rr][g];
+                }
+        });
+        // the exchanged column: -col / pivot for the other rows, 1 / pivot for the pivot row
+        reg_set<LD>(T0, cj, own ? inv : -colr[0] * inv);
+#pragma unroll
+        for (int rr = 1; rr < RPL; ++rr) {
+            const int r = lane + 32 * rr;
+            if (r < nb && r != l && colr[rr] != 0.0) Dr[rr][cj] = -colr[rr] * inv;
+        }
+        __syncwarp();
+        if (!l_in_regs)
+            for (int k = lane; k < LD; k += 32) Dl[k] = (k == cj) ? inv : q[k];
+        if (lane == 0) k2w_swap_labels(c, l, j);
+        const bool ok = __all_sync(PPG_FULL, okb);
+        __syncwarp();
+        return ok;
+    }
+};
+
 // ---- storage policy B: the dictionary in REGISTERS - lane (r & 31) holds basic row r in slot r >> 5, DC = columns incl.
 // the right-hand side (exactly wk_ld).  Only the scaled pivot row crosses shared memory (DC doubles per pivot); the rank-1
 // update is RPL x DC back-to-back DFMAs on registers.  Register arrays are only ever indexed by compile-time constants
@@ -248,6 +391,7 @@ template <int RPL_, int DC>
 struct K2wRegDict {
     static constexpr int RPL = RPL_;
     static constexpr bool IN_SMEM = false;
+    static constexpr int SMEM_ROW0 = 0;
     double T[RPL][DC];
     __device__ __forceinline__ void reload(const DevProgram& P, const K2wCtx& c, int lane) {
         static_for<RPL>([&](auto RR) {
@@ -420,6 +564,12 @@ __device__ __forceinline__ int k2w_mark_row(const K2wCtx& c, uint8_t* __restrict
     return got;
 }
 
+template <class Dict>
+__host__ __device__ constexpr size_t k2w_dict_smem_bytes(int nb, int lds) {
+    if constexpr (!Dict::IN_SMEM) return 0;
+    else return (size_t)(nb > Dict::SMEM_ROW0 ? nb - Dict::SMEM_ROW0 : 0) * lds * 8;
+}
+
 // One walker = one warp.  Work item = the candidate groups (prefix, second-last row) that START in a range of `chunk`
 // candidates.
 template <class Dict>
@@ -435,7 +585,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
     c.nb = P.wk_nb; c.nf = P.nfree; c.ld = P.wk_ld; c.lds = lds; c.R0 = P.R0; c.W4 = W4;
     {
         unsigned char* base = k2w_smem + (size_t)warp * walker_bytes;
-        c.D = reinterpret_cast<double*>(base); if (Dict::IN_SMEM) base += (size_t)c.nb * lds * 8;
+        c.D = reinterpret_cast<double*>(base); base += k2w_dict_smem_bytes<Dict>(c.nb, lds);
         c.prow = reinterpret_cast<double*>(base); base += (size_t)lds * 8;
         c.orig = reinterpret_cast<uint64_t*>(base); base += (size_t)c.R0 * W4 * 8;
         c.todo = reinterpret_cast<uint64_t*>(base); base += (size_t)c.R0 * W4 * 8;
@@ -685,7 +835,7 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
                                 unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st,
                                 bool* handled) {
     const int nb = P.wk_nb, ld = P.wk_ld, lds = ld | 1, W4 = (P.R0 + 63) / 64;
-    size_t wb = (Dict::IN_SMEM ? (size_t)nb * lds * 8 : 0) + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
+    size_t wb = k2w_dict_smem_bytes<Dict>(nb, lds) + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
                 (size_t)(nb + P.nfree + 2 * P.R0 + K2W_MAXFIX + 2) * 4;
     wb = (wb + 15) & ~(size_t)15;
     auto kern = k2w_walk_kernel<Dict>;
@@ -739,7 +889,12 @@ cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, 
     // the shared-memory dictionary (1395 vs 535 ms on levels 4-5); kept because it decides identically and is the
     // starting point for a leaner version
     if (regs_on && rpl == 3 && P.wk_ld == 37) K2W_GO(K2wRegDict<3 K2W_COMMA 37>);
-    if (rpl == 3 && P.wk_ld == 37) K2W_GO(K2wSmemDict<3 K2W_COMMA 37>);   // the bench shape, columns known at compile time
+    // (measured on levels 1..5: 317 ms against 240 ms with everything in shared memory - the register row saves 36 % of the
+    // shared-memory wavefronts but pays for it with register-select code (reg_pick / reg_set jump tables, 37 selects for the
+    // pivot row's owner, a serial scan of the target row): an EXPERIMENT, off by default like policy B)
+    static const int hybrid_on = getenv("PPGPU_K2W_HYBRID") ? atoi(getenv("PPGPU_K2W_HYBRID")) : 0;
+    if (hybrid_on && rpl == 3 && P.wk_ld == 37) K2W_GO(K2wHybridDict<3 K2W_COMMA 37>);   // the bench shape: row slot 0 in registers
+    if (rpl == 3 && P.wk_ld == 37) K2W_GO(K2wSmemDict<3 K2W_COMMA 37>);   // ... everything in shared memory, columns known at compile time
     switch (rpl) {
         case 1: K2W_GO(K2wSmemDict<1>);
         case 2: K2W_GO(K2wSmemDict<2>);
