@@ -462,6 +462,8 @@ def run_gpu(args, rank, world, local_rank):
                      'flop_model': 'useful fp64 FMAs counted in-kernel: K2w pivots x basic rows x columns of the slack dictionary '
                                    '(rank-1 update); K2a relaxation steps x R0 x 3; K2/K4 pivots x live rows x columns',
                      'k2w': {'certified': counters['k2w_certified'], 'pivots': counters['k2w_pivots'], 'gave_up': counters['k2w_giveup']},
+                     'inherited': {'certified': counters['inherited'], 'lookups': counters['inherit_lookups'],
+                                   'note': 'candidates certified by the witness vertex of one of their parents (no LP work)'},
                      'shared_memory': smem,
                      'k2a': {'tried': counters['k2a_tried'], 'certified': counters['k2a_certified'], 'steps': counters['k2a_steps']},
                      'k2': {'lps': counters['k2_lps'], 'pivots': counters['k2_pivots']},

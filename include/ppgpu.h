@@ -64,7 +64,7 @@ int ppgpu_program_info(const ppgpu_program* prog, ppgpu_info* out);
 
 /* Engine knobs of one handle (no reference counterpart: the reference has one LP call per candidate and nothing to tune).
  *   PPGPU_OPT_K2W_MIN  smallest number of candidates per ppgpu_level_eval chunk for which the feasibility certificates are
- *                      produced by the vertex walk (csrc/k2w_walk.cu) before the relaxation (default 500000; 0: always;
+ *                      produced by the vertex walk (csrc/k2w_walk.cu) before the relaxation (default 100000; 0: always;
  *                      negative: never).  Decisions do not depend on it - only which kernel exhibits the feasible point. */
 #define PPGPU_OPT_K2W_MIN 0
 int ppgpu_set_option(ppgpu_program* prog, int32_t option, int64_t value);
@@ -82,6 +82,20 @@ int ppgpu_root_level(ppgpu_program* prog, uint64_t* d_masks, int64_t* h_count, p
  * handles); d_masks / d_status may be arbitrary sub-ranges of a level (that is how a level is sharded between GPUs). */
 int ppgpu_level_eval(ppgpu_program* prog, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
                      int32_t stages, ppgpu_stream stream);
+
+/* ppgpu_level_eval with feasibility WITNESSES (no reference counterpart: the reference solves one LP per candidate,
+ * mplp_program.py:411-444, and shares nothing between candidates or levels).
+ *   d_witness      (n x words uint64, zero-initialised by the caller, or NULL) receives, for every candidate certified by
+ *                  the vertex walk or by inheritance, the mask of ALL rows active at the certifying vertex;
+ *   d_parent_*     (or NULL / 0) describe the level the candidates were generated from: the feasible masks and the
+ *                  workspace exactly as ppgpu_children_count / ppgpu_children_prepare left them (the workspace holds the
+ *                  hash set of those masks), and the witnesses of those parents in the same order.  A candidate one of
+ *                  whose parents has a witness that also holds the added row is certified by that same vertex before any
+ *                  LP work is spent on it (and passes the witness on).
+ * Decisions are identical with and without witnesses; only which kernel exhibits the feasible point changes. */
+int ppgpu_level_eval_w(ppgpu_program* prog, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
+                       int32_t stages, uint64_t* d_witness, const uint64_t* d_parent_feas, int64_t parent_nf,
+                       const void* d_parent_ws, const uint64_t* d_parent_wit, ppgpu_stream stream);
 
 /* Ordered compaction: ascending indices i with (d_status[i] & bits) == value.  Synchronises the stream to return the
  * count.  d_ws must hold ppgpu_scan_workspace_bytes(n) bytes. */
@@ -155,9 +169,9 @@ int64_t ppgpu_launch_count(const ppgpu_program* prog);
 
 /* Optional per-kernel-family timing with CUDA events recorded on the launch stream (used by bench.py for the
  * roofline line).  Families: 0 K1 rank, 1 K2 feasibility LP, 2 K3/K4 screen, 3 K5 emission, 4 K6 count, 5 K6 write,
- * 6 ordered compaction, 7 K2a relaxation certificates, 8 K2w vertex-walk certificates.  h_ms / h_launches hold
- * PPGPU_NUM_FAMILIES entries. */
-#define PPGPU_NUM_FAMILIES 9
+ * 6 ordered compaction, 7 K2a relaxation certificates, 8 K2w vertex-walk certificates, 9 certificates inherited from the
+ * parents' witnesses.  h_ms / h_launches hold PPGPU_NUM_FAMILIES entries. */
+#define PPGPU_NUM_FAMILIES 10
 int ppgpu_profile_enable(ppgpu_program* prog, int32_t on);
 int ppgpu_profile_read(ppgpu_program* prog, double* h_ms, int64_t* h_launches, int32_t reset);
 

@@ -816,8 +816,12 @@ struct WalkDict {
     }
 };
 
-// certified[i] = 1 for every candidate the walk certifies; returns the number of pivots
-long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std::vector<char>& certified) {
+// certified[i] = 1 for every candidate the walk certifies; returns the number of pivots.
+// witness (n x W4 words, optional): the mask of ALL rows nonbasic at the vertex that certified candidate i - what the kernel
+// leaves for the next level (k6_children.cu::inherit_kernel: a child one of whose parents has a witness holding the added
+// row too is certified by that same vertex).  W4 = ceil(R0 / 64).
+long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std::vector<char>& certified,
+                    uint64_t* witness = nullptr) {
     certified.assign(n, 0);
     if (!P.wk_ok || n == 0) return 0;
     std::vector<std::vector<int>> acts(n);
@@ -843,7 +847,16 @@ long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std:
             for (int y = 0; y < P.R0; ++y) {
                 if (!wd.nonbasic(y)) continue;
                 const int a = std::min(r, y), b = std::max(r, y);
-                if (open[a][b] >= 0) { certified[open[a][b]] = 1; open[a][b] = -1; }
+                if (open[a][b] >= 0) {
+                    certified[open[a][b]] = 1;
+                    if (witness) {
+                        const int W4 = (P.R0 + 63) / 64;
+                        uint64_t* wq = witness + (size_t)W4 * open[a][b];
+                        for (int w = 0; w < W4; ++w) wq[w] = 0;
+                        for (int j = 0; j < wd.nf; ++j) wq[wd.nvar[j] >> 6] |= 1ull << (wd.nvar[j] & 63);
+                    }
+                    open[a][b] = -1;
+                }
             }
         };
         bool restart = wd.pivots > 3000 || !wd.ok;
@@ -982,6 +995,13 @@ int twin_walk_dict(void* h, int* nb, int* ld, double* D0, int* bvar, int* nvar) 
 long twin_k2w(void* h, const uint64_t* masks, long ncand, uint8_t* certified) {
     std::vector<char> c;
     const long piv = k2w_walk_level(((Twin*)h)->P, masks, ncand, c);
+    for (long i = 0; i < ncand; ++i) certified[i] = (uint8_t)c[i];
+    return piv;
+}
+// ... with the witnesses (ncand x ceil(R0 / 64) words, zero where the walk certified nothing)
+long twin_k2w_witness(void* h, const uint64_t* masks, long ncand, uint8_t* certified, uint64_t* witness) {
+    std::vector<char> c;
+    const long piv = k2w_walk_level(((Twin*)h)->P, masks, ncand, c, witness);
     for (long i = 0; i < ncand; ++i) certified[i] = (uint8_t)c[i];
     return piv;
 }

@@ -136,6 +136,18 @@ class Twin:
         piv = l.twin_k2w(self.h, masks.ctypes.data, masks.shape[0], cert.ctypes.data)
         return cert, int(piv)
 
+    def k2w_witness(self, masks):
+        """sequential K2w with witnesses: (certified flags, pivots, witness masks n x ceil(R0 / 64) uint64) - the witness of a
+        certified candidate is the set of all rows active at the certifying vertex"""
+        l = lib()
+        l.twin_k2w_witness.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]
+        l.twin_k2w_witness.restype = ctypes.c_long
+        masks = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(-1, self.W)
+        cert = numpy.zeros(masks.shape[0], dtype=numpy.uint8)
+        wit = numpy.zeros((masks.shape[0], (self.R0 + 63) // 64), dtype=numpy.uint64)
+        piv = l.twin_k2w_witness(self.h, masks.ctypes.data, masks.shape[0], cert.ctypes.data, wit.ctypes.data)
+        return cert, int(piv), wit
+
     def pivots(self):
         return lib().twin_pivots(self.h)
 

@@ -7,11 +7,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libppgpu.so')
 
 NUM_COUNTERS = 24
-NUM_FAMILIES = 9
-FAMILY_NAMES = ('k1_rank', 'k2_feas_lp', 'k34_kkt_cheb', 'k5_emit', 'k6_count', 'k6_write', 'select', 'k2a_relax', 'k2w_walk')
+NUM_FAMILIES = 10
+FAMILY_NAMES = ('k1_rank', 'k2_feas_lp', 'k34_kkt_cheb', 'k5_emit', 'k6_count', 'k6_write', 'select', 'k2a_relax', 'k2w_walk', 'inherit')
 COUNTER_NAMES = ('k1_candidates', 'k2_lps', 'k2_pivots', 'k2_work', 'k4_lps', 'k4_pivots', 'k4_work', 'k5_lps',
                  'k5_pivots', 'k5_work', 'numeric', 'border', 'k6_lookups', 'k2a_tried', 'k2a_certified', 'k2a_steps', 'k2a_work',
-                 'k2w_certified', 'k2w_pivots', 'k2w_work', 'k2w_giveup')
+                 'k2w_certified', 'k2w_pivots', 'k2w_work', 'k2w_giveup', 'inherited', 'inherit_lookups')
 
 # status bits (csrc/tolerances.h)
 ST_RANK, ST_FEAS, ST_OPT, ST_REGION, ST_BORDER, ST_NUMERIC, ST_THIN = 1, 2, 4, 8, 16, 32, 64
@@ -38,6 +38,7 @@ SYMBOLS = {
     'ppgpu_set_option': (ctypes.c_int, [_vp, _i32, _i64]),
     'ppgpu_root_level': (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_i64), _vp]),
     'ppgpu_level_eval': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
+    'ppgpu_level_eval_w': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     'ppgpu_scan_workspace_bytes': (_sz, [_i64]),
     'ppgpu_level_select': (ctypes.c_int, [_vp, _vp, _i64, _u8, _u8, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp]),
     'ppgpu_regions_emit': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -35,7 +35,7 @@ struct ppgpu_program {
     double* d_warm_resid = nullptr;
     long long* d_warm_idx = nullptr;
     unsigned long long* d_warm_count = nullptr;
-    long long k2w_min = 500000;   // smallest launch the vertex walk (K2w) is used for (ppgpu_set_option)
+    long long k2w_min = 100000;   // smallest launch the vertex walk (K2w) is used for (ppgpu_set_option)
     double prof_ms[PPGPU_NUM_FAMILIES] = {0};
     long long prof_launches[PPGPU_NUM_FAMILIES] = {0};
 };
@@ -248,8 +248,17 @@ static cudaError_t ensure_warm(ppgpu_program* p, long long cap, cudaStream_t st)
     return cudaSuccess;
 }
 
+// what ppgpu_level_eval_w adds to a level evaluation (all optional)
+struct WitnessIo {
+    uint64_t* out = nullptr;                 // n x W: witness of every candidate the walk certifies / that inherits one
+    const uint64_t* parent_feas = nullptr;   // parent level: feasible masks (nf x W), K6 workspace with their hash set,
+    long long parent_nf = 0;                 // and the witnesses of those parents in the same order
+    const void* parent_ws = nullptr;
+    const uint64_t* parent_wit = nullptr;
+};
+
 static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
-                            int32_t stages, cudaStream_t st) {
+                            int32_t stages, cudaStream_t st, const WitnessIo& wio) {
     cudaError_t e;
     if (stages & 1) {
         ProfScope ps(p, st, 0);
@@ -265,13 +274,21 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
             if (k_act >= 2 && k_act <= p->dev.np) p->launches++;   // singular-value re-check of borderline decisions
         }
     }
+    if ((stages & 2) && !(stages & 8) && wio.parent_feas && wio.parent_wit && wio.parent_ws && wio.parent_nf > 0) {
+        // certificates inherited from the parents' witness vertices: what they cover never reaches the walk
+        ProfScope ps(p, st, 9);
+        e = launch_inherit(p->dev, d_masks, n, d_status, wio.out, wio.parent_feas, wio.parent_nf, wio.parent_ws,
+                           wio.parent_wit, p->d_counters, st);
+        if (e != cudaSuccess) return fail("witness inheritance", e);
+        p->launches++;
+    }
     static const int warm_on = getenv("PPGPU_WARM") ? atoi(getenv("PPGPU_WARM")) : 1;
     p->dev.warm_count = nullptr; p->dev.warm_resid = nullptr; p->dev.warm_idx = nullptr; p->dev.warm_cap = 0;
     if ((stages & 2) && !(stages & 8) && k_act >= 1 && p->k2w_min >= 0 && n >= p->k2w_min) {
         // certificates shared between the candidates of a prefix (vertex walk); the relaxation only sees what is left
         ProfScope ps(p, st, 8);
         bool handled = false;
-        e = launch_k2w(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st, &handled);
+        e = launch_k2w(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st, &handled, wio.out);
         if (e != cudaSuccess) return fail("K2w vertex walk", e);
         if (handled) p->launches++;
     }
@@ -322,14 +339,23 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
 
 int ppgpu_level_eval(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
                      int32_t stages, ppgpu_stream stream) {
+    return ppgpu_level_eval_w(p, d_masks, n, k_act, d_status, stages, nullptr, nullptr, 0, nullptr, nullptr, stream);
+}
+
+int ppgpu_level_eval_w(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
+                       int32_t stages, uint64_t* d_witness, const uint64_t* d_parent_feas, int64_t parent_nf,
+                       const void* d_parent_ws, const uint64_t* d_parent_wit, ppgpu_stream stream) {
     if (!p) return fail_msg("null argument");
     if (n <= 0) return 0;
+    WitnessIo wio;
+    wio.parent_feas = d_parent_feas; wio.parent_nf = parent_nf; wio.parent_ws = d_parent_ws; wio.parent_wit = d_parent_wit;
     const bool walk = (stages & 2) && !(stages & 8) && k_act >= 1 && p->dev.wk_ok && p->k2w_min >= 0 && n >= p->k2w_min;
     const long long chunk = walk ? walk_chunk() : level_chunk();
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t nn = n - off < chunk ? n - off : chunk;
+        wio.out = d_witness ? d_witness + (size_t)off * p->dev.W : nullptr;
         const int rc = level_eval_chunk(p, d_masks + (size_t)off * p->dev.W, nn, k_act, d_status + off, stages,
-                                        (cudaStream_t)stream);
+                                        (cudaStream_t)stream, wio);
         if (rc) return rc;
     }
     return 0;

@@ -47,6 +47,7 @@ enum Counter {
     CNT_K2A_WORK,                                     // 16: steps x R0 x (1 + k') useful FMAs
     CNT_K2W_CERTIFIED, CNT_K2W_PIVOTS, CNT_K2W_WORK,  // 17, 18, 19: vertex walk (pivots x basic rows x columns FMAs)
     CNT_K2W_GIVEUP,                                   // 20: drives abandoned (iteration cap, empty face, dependent row)
+    CNT_INHERITED, CNT_INHERIT_LOOKUPS,               // 21, 22: certificates inherited from parent witnesses / hash look-ups
     CNT_COUNT = 24
 };
 

@@ -49,7 +49,8 @@ struct K2wCtx {
     int* rowstart;    // R0         position in the segment of the first candidate with second-last row a
     uint64_t* nbm;    // W4         bitmask of the nonbasic rows
     int* fixrow;      // K2W_MAXFIX rows of the prefix currently fixed, in order
-    int nb, nf, ld, lds, R0, W4;
+    uint64_t* witness; // n x Wm (global, may be null): nonbasic-row mask of the vertex that certified a candidate
+    int nb, nf, ld, lds, R0, W4, Wm;
 };
 
 __device__ __forceinline__ int k2w_top_bit(const uint64_t* m, int W, int* second) {
@@ -498,6 +499,10 @@ __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict
     // fire-and-forget OR on the aligned word that holds the byte (a load + store would stall the walker for an L2 round trip)
     const uintptr_t addr = reinterpret_cast<uintptr_t>(status + idx);
     atomicOr(reinterpret_cast<unsigned*>(addr & ~(uintptr_t)3), (unsigned)PPG_ST_FEAS << (8u * (unsigned)(addr & 3)));
+    // the WITNESS: the rows active at the certifying vertex.  Every superset of the candidate inside this mask is certified
+    // by the same vertex - the next level inherits it (k6_children.cu::inherit_kernel) instead of walking again
+    if (c.witness)
+        for (int w = 0; w < c.Wm; ++w) c.witness[idx * c.Wm + w] = c.nbm[w];
 }
 
 // bits of word w with index >= a
@@ -576,13 +581,14 @@ template <class Dict>
 __global__ void __launch_bounds__(256, 1)
 k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int chunk,
-                int walker_bytes, int lds, int W4, int group_items, int split_len) {
+                int walker_bytes, int lds, int W4, int group_items, int split_len, uint64_t* __restrict__ witness) {
     extern __shared__ unsigned char k2w_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int RPL = Dict::RPL;
     Dict dict;
     K2wCtx c;
     c.nb = P.wk_nb; c.nf = P.nfree; c.ld = P.wk_ld; c.lds = lds; c.R0 = P.R0; c.W4 = W4;
+    c.witness = witness; c.Wm = P.W;
     {
         unsigned char* base = k2w_smem + (size_t)warp * walker_bytes;
         c.D = reinterpret_cast<double*>(base); base += k2w_dict_smem_bytes<Dict>(c.nb, lds);
@@ -833,7 +839,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
 template <class Dict>
 static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                                 unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st,
-                                bool* handled) {
+                                bool* handled, uint64_t* witness) {
     const int nb = P.wk_nb, ld = P.wk_ld, lds = ld | 1, W4 = (P.R0 + 63) / 64;
     size_t wb = k2w_dict_smem_bytes<Dict>(nb, lds) + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
                 (size_t)(nb + P.nfree + 2 * P.R0 + K2W_MAXFIX + 2) * 4;
@@ -870,20 +876,21 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
     static const int split_len = getenv("PPGPU_K2W_SPLIT") ? atoi(getenv("PPGPU_K2W_SPLIT")) : 2048;
     const int group_items = groups_env >= 0 ? groups_env : (n / walkers < 16384 ? 1 : 0);
     kern<<<(unsigned)grid, 32 * wpc, smem, st>>>(P, masks, n, k_act, status, queue, counters, (int)chunk, (int)wb, lds, W4,
-                                                 group_items, split_len);
+                                                 group_items, split_len, witness);
     *handled = true;
     return cudaGetLastError();
 }
 
 // *handled == false: the walk is off for this program / level (no vertex dictionary, prefix too long, dictionary too large)
 cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
-                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled) {
+                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled,
+                       uint64_t* witness) {
     *handled = false;
     static const int on = getenv("PPGPU_K2W") ? atoi(getenv("PPGPU_K2W")) : 1;
     static const int regs_on = getenv("PPGPU_K2W_REG") ? atoi(getenv("PPGPU_K2W_REG")) : 0;
     if (!on || !P.wk_ok || k_act < 1 || k_act - 2 > K2W_MAXFIX || P.W > 4 || P.nfree > 64) return cudaSuccess;
     const int rpl = (P.wk_nb + 31) / 32;
-#define K2W_GO(D) return launch_k2w_t<D>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled)
+#define K2W_GO(D) return launch_k2w_t<D>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled, witness)
     // The register-resident dictionary (instantiated for the 100 x 30 x 6 bench program: 76 basic rows x 37 columns) is
     // an EXPERIMENT, off by default (PPGPU_K2W_REG=1): 255 registers + 2 KB of spills, measured 2.6x slower per pivot than
     // the shared-memory dictionary (1395 vs 535 ms on levels 4-5); kept because it decides identically and is the

@@ -382,6 +382,103 @@ cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, cons
     return cudaGetLastError();
 }
 
+// ---- certificates inherited from the previous level ------------------------------------------------------------------------
+// The vertex walk (k2w_walk.cu) leaves, for every candidate it certifies, the WITNESS: the mask of all rows active at the
+// certifying vertex (~n' rows, the candidate's own among them).  A candidate C of the next level is feasible as soon as the
+// witness of ONE of its parents C \ {b} also has row b active: the same vertex, the same exact statement ("the rows of C
+// are nonbasic at a vertex whose basic slacks are >= -1e-8").  Measured on the 100x30x6 program (CPU model of the walk):
+// 76 % of the level-5 candidates are certified by one of their five parents' witnesses, which removes them - the ones that
+// are easy to reach - from the walk.  Parents are found in the open-addressing hash set K6 built when it generated this
+// level (children_prepare: table slots -> index into the parent level's feasible list); parent_wit is the witness array
+// gathered in that order.  One thread per candidate; rows are dropped from the highest down (measured: the middle
+// positions inherit most often, the first one least).  An inherited witness is passed on (witness_out), so that
+// certificates propagate down the levels without any further pivot.
+__device__ __forceinline__ int hash_find(const uint64_t* __restrict__ feas, int W, const int* __restrict__ table,
+                                         unsigned cap_mask, const Mask4& key) {
+    unsigned slot = hash_mask(key, W) & cap_mask;
+    for (;;) {
+        const int e = __ldg(table + slot);
+        if (e < 0) return -1;
+        bool same = true;
+#pragma unroll
+        for (int x = 0; x < MAXW; ++x)
+            if (x < W && feas[(long long)e * W + x] != key.w[x]) same = false;
+        if (same) return e;
+        slot = (slot + 1) & cap_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+inherit_kernel(int W, const uint64_t* __restrict__ masks, long long n, uint8_t* __restrict__ status,
+               uint64_t* __restrict__ witness_out, const uint64_t* __restrict__ pfeas, const int* __restrict__ table,
+               unsigned cap_mask, const uint64_t* __restrict__ pwit, unsigned long long* __restrict__ counters) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long lookups = 0;
+    int got = 0;
+    if (i < n) {
+        const uint8_t sb = status[i];
+        if ((sb & PPG_ST_RANK) && !(sb & PPG_ST_FEAS)) {
+            Mask4 m;
+#pragma unroll
+            for (int x = 0; x < MAXW; ++x) m.w[x] = x < W ? masks[i * W + x] : 0ull;
+#pragma unroll
+            for (int w = MAXW - 1; w >= 0; --w) {
+                if (w < W && !got) {
+                    uint64_t bits = m.w[w];
+                    while (bits && !got) {
+                        const int b = 63 - __clzll((long long)bits);
+                        bits &= ~(1ull << b);
+                        Mask4 sub = m;
+#pragma unroll
+                        for (int x = 0; x < MAXW; ++x)
+                            if (x == w) sub.w[x] &= ~(1ull << b);
+                        ++lookups;
+                        const int e = hash_find(pfeas, W, table, cap_mask, sub);
+                        if (e < 0) continue;   // (cannot happen for a child K6 let through: every parent is feasible)
+                        // the parent's witness holds the parent (or is empty: certified by the relaxation / the simplex)
+                        bool inside = true;
+                        uint64_t wv[MAXW];
+#pragma unroll
+                        for (int x = 0; x < MAXW; ++x) {
+                            wv[x] = x < W ? __ldg(pwit + (long long)e * W + x) : 0ull;
+                            if (m.w[x] & ~wv[x]) inside = false;
+                        }
+                        if (inside) {
+                            got = 1;
+                            status[i] = sb | PPG_ST_FEAS;
+                            if (witness_out)
+#pragma unroll
+                                for (int x = 0; x < MAXW; ++x)
+                                    if (x < W) witness_out[i * W + x] = wv[x];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    got = __reduce_add_sync(0xffffffffu, got);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lookups += __shfl_xor_sync(0xffffffffu, lookups, o);
+    if ((threadIdx.x & 31) == 0 && lookups) {
+        atomicAdd(&counters[CNT_INHERITED], (unsigned long long)got);
+        atomicAdd(&counters[CNT_INHERIT_LOOKUPS], lookups);
+    }
+}
+
+cudaError_t launch_inherit(const DevProgram& P, const uint64_t* masks, long long n, uint8_t* status, uint64_t* witness_out,
+                           const uint64_t* parent_feas, long long parent_nf, const void* parent_ws, const uint64_t* parent_wit,
+                           unsigned long long* counters, cudaStream_t st) {
+    if (n <= 0 || parent_nf <= 0) return cudaSuccess;
+    if (P.W > MAXW) return cudaErrorInvalidValue;
+    // the table sits in the K6 workspace behind the scan scratch (children_prepare)
+    const long long nb = (parent_nf + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const unsigned cap = hash_capacity(parent_nf);
+    const int* table = reinterpret_cast<const int*>((const long long*)parent_ws + nb + 2);
+    inherit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.W, masks, n, status, witness_out, parent_feas, table, cap - 1,
+                                                                parent_wit, counters);
+    return cudaGetLastError();
+}
+
 // ---- FP64 FMA peak of the device (roofline denominator for the LP kernels; not in MEASURED_PEAKS.json)
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

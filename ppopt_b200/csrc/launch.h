@@ -33,8 +33,15 @@ cudaError_t launch_k2a_prefix(const DevProgram& P, const uint64_t* masks, long l
                               unsigned long long* queue, unsigned long long* counters, int max_iter, int sm_count,
                               cudaStream_t st, bool* handled);
 // K2w: feasibility certificates shared between the candidates of a prefix by a primal-simplex walk over vertices
+// witness (n x W, may be null): receives the active-row mask of the vertex that certified a candidate
 cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
-                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled);
+                       unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled,
+                       uint64_t* witness);
+// certificates INHERITED from the previous level: a candidate is feasible when the witness vertex of one of its parents
+// (candidate minus one row, looked up in the hash set K6 built for that level) has the dropped row active as well
+cudaError_t launch_inherit(const DevProgram& P, const uint64_t* masks, long long n, uint8_t* status, uint64_t* witness_out,
+                           const uint64_t* parent_feas, long long parent_nf, const void* parent_ws, const uint64_t* parent_wit,
+                           unsigned long long* counters, cudaStream_t st);
 cudaError_t launch_k34(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st);
 cudaError_t launch_k34_compact(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,

@@ -102,14 +102,27 @@ class Engine:
         return masks[:cnt.value]
 
     def level_eval(self, masks: torch.Tensor, k_act: int, status: Optional[torch.Tensor] = None, stages: int = 7,
-                   lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+                   lo: int = 0, hi: Optional[int] = None, witness: Optional[torch.Tensor] = None,
+                   parent: Optional['ParentLevel'] = None) -> torch.Tensor:
+        """status bytes of masks[lo:hi].  ``witness`` (n x W int64, zeros): receives the active-row mask of the vertex
+        that certified a candidate; ``parent``: the level the candidates were generated from (feasible masks, their hash
+        set, their witnesses) - candidates covered by a parent's witness are certified without any LP work
+        (ppgpu_level_eval_w)."""
         n = masks.shape[0]
         if status is None:
             status = torch.zeros((n,), dtype=torch.uint8, device=self.tdev)
         hi = n if hi is None else hi
         if hi > lo:
-            _lib.check(self.lib.ppgpu_level_eval(self.h, masks.data_ptr() + lo * self.W * 8, hi - lo, k_act,
-                                                 status.data_ptr() + lo, stages, self._stream()), 'level_eval')
+            if witness is None and parent is None:
+                _lib.check(self.lib.ppgpu_level_eval(self.h, masks.data_ptr() + lo * self.W * 8, hi - lo, k_act,
+                                                     status.data_ptr() + lo, stages, self._stream()), 'level_eval')
+            else:
+                pf, pnf, pws, pw = (parent.feas_masks.data_ptr(), parent.nf, parent.ws.data_ptr(), parent.wit.data_ptr()) \
+                    if parent is not None else (None, 0, None, None)
+                _lib.check(self.lib.ppgpu_level_eval_w(self.h, masks.data_ptr() + lo * self.W * 8, hi - lo, k_act,
+                                                       status.data_ptr() + lo, stages,
+                                                       None if witness is None else witness.data_ptr() + lo * self.W * 8,
+                                                       pf, pnf, pws, pw, self._stream()), 'level_eval_w')
         return status
 
     def select(self, status: torch.Tensor, bits: int, value: int) -> torch.Tensor:
@@ -136,14 +149,16 @@ class Engine:
                                                self._stream()), 'regions_emit')
         return laws, rows, flags, info
 
-    def children(self, masks: torch.Tensor, feas_idx: torch.Tensor, k_act: int, dist=None) -> torch.Tensor:
+    def children(self, masks: torch.Tensor, feas_idx: torch.Tensor, k_act: int, dist=None, keep: Optional[dict] = None) -> torch.Tensor:
         """next level's candidates; with dist (torch.distributed, world > 1) the pruning look-ups of the parents are split
-        between the ranks and the per-parent results summed (every rank ends up with the identical child array)"""
+        between the ranks and the per-parent results summed (every rank ends up with the identical child array).
+        ``keep`` (dict) receives the gathered feasible masks and the workspace holding their hash set: what the next
+        level needs to look its candidates' parents up (witness inheritance)"""
         nf = feas_idx.shape[0]
         if nf == 0:
             return self.empty((0, self.W), torch.int64)
         if dist is not None and dist.get_world_size() > 1 and nf >= 65536:
-            return self._children_sharded(masks, feas_idx, k_act, dist)
+            return self._children_sharded(masks, feas_idx, k_act, dist, keep)
         feas_masks = self.empty((nf, self.W), torch.int64)
         survive = self.empty((nf, self.W), torch.int64)
         offsets = self.empty((nf + 1,), torch.int64)
@@ -154,13 +169,15 @@ class Engine:
                                                  feas_masks.data_ptr(), survive.data_ptr(), offsets.data_ptr(),
                                                  ctypes.byref(tot), ws.data_ptr(), ws_bytes, self._stream()),
                    'children_count')
+        if keep is not None:
+            keep.update(feas_masks=feas_masks, ws=ws, nf=nf)
         out = self.empty((tot.value, self.W), torch.int64)
         if tot.value:
             _lib.check(self.lib.ppgpu_children_write(self.h, feas_masks.data_ptr(), survive.data_ptr(), offsets.data_ptr(),
                                                      nf, out.data_ptr(), self._stream()), 'children_write')
         return out
 
-    def _children_sharded(self, masks, feas_idx, k_act, dist):
+    def _children_sharded(self, masks, feas_idx, k_act, dist, keep=None):
         from . import sharding
         nf = feas_idx.shape[0]
         feas_masks = self.empty((nf, self.W), torch.int64)
@@ -170,6 +187,8 @@ class Engine:
         ws = self.empty(((ws_bytes + 7) // 8,), torch.int64)
         _lib.check(self.lib.ppgpu_children_prepare(self.h, masks.data_ptr(), feas_idx.data_ptr(), nf, feas_masks.data_ptr(),
                                                    ws.data_ptr(), ws_bytes, self._stream()), 'children_prepare')
+        if keep is not None:
+            keep.update(feas_masks=feas_masks, ws=ws, nf=nf)
         for lo, hi in sharding.chunks(nf, dist.get_rank(), dist.get_world_size()):
             _lib.check(self.lib.ppgpu_children_count_range(self.h, feas_masks.data_ptr(), nf, k_act, survive.data_ptr(),
                                                            counts.data_ptr(), lo, hi, ws.data_ptr(), ws_bytes,
@@ -328,6 +347,24 @@ def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, in
     return out
 
 
+class ParentLevel:
+    """What a level leaves behind for the next one (witness inheritance): its feasible masks in K6's order, the K6 workspace
+    holding their hash set, and the witnesses (active-row masks of the certifying vertices) in the same order."""
+    __slots__ = ('feas_masks', 'ws', 'nf', 'wit')
+
+    def __init__(self, feas_masks, ws, nf, wit):
+        self.feas_masks, self.ws, self.nf, self.wit = feas_masks, ws, int(nf), wit
+
+
+# levels below this size are neither walked nor worth a witness array (PPGPU_OPT_K2W_MIN's default)
+WITNESS_MIN_LEVEL = 100000
+
+
+def _inherit_on() -> bool:
+    import os
+    return os.environ.get('PPGPU_INHERIT', '1') != '0'
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -349,27 +386,34 @@ def _checksum(status: torch.Tensor) -> int:
     return int((((status & 15).to(torch.int64) + 1) * w).sum().item() & 0x7fffffffffffffff)
 
 
-def _eval_level(eng: Engine, masks: torch.Tensor, k_act: int, dist, rank: int, world: int) -> torch.Tensor:
+def _eval_level(eng: Engine, masks: torch.Tensor, k_act: int, dist, rank: int, world: int,
+                wit: Optional[torch.Tensor] = None, parent: Optional['ParentLevel'] = None) -> torch.Tensor:
     """status bytes of one level.  Multi-GPU: this rank's chunks (sharding.py) are packed into ONE contiguous array, so
     that every stage is one launch per rank (16 chunk-wise calls x 7 launches paid 16 kernel tails each), evaluated, and
-    the bytes scattered back; one NCCL all-reduce(SUM) of the byte vector then gives every rank all statuses."""
+    the bytes scattered back; one NCCL all-reduce(SUM) of the byte vector then gives every rank all statuses (and, when
+    witnesses are collected, one more of the witness words: disjoint supports, the sum is the union)."""
     n = masks.shape[0]
     status = torch.zeros((n,), dtype=torch.uint8, device=eng.tdev)
     if world <= 1:
-        eng.level_eval(masks, k_act, status, 7)
+        eng.level_eval(masks, k_act, status, 7, witness=wit, parent=parent)
         return status
     mine = sharding.chunks(n, rank, world)
     if mine:
         if len(mine) == 1:
             lo, hi = mine[0]
-            eng.level_eval(masks, k_act, status, 7, lo, hi)
+            eng.level_eval(masks, k_act, status, 7, lo, hi, witness=wit, parent=parent)
         else:
             packed = torch.cat([masks[lo:hi] for lo, hi in mine])
-            st = eng.level_eval(packed, k_act, None, 7)
+            wp = torch.zeros_like(packed) if wit is not None else None
+            st = eng.level_eval(packed, k_act, None, 7, witness=wp, parent=parent)
             off = 0
             for lo, hi in mine:
                 status[lo:hi] = st[off:off + hi - lo]
+                if wit is not None:
+                    wit[lo:hi] = wp[off:off + hi - lo]
                 off += hi - lo
+    if wit is not None:
+        dist.all_reduce(wit, op=dist.ReduceOp.SUM)
     return sharding.gather_status(status, dist)
 
 
@@ -441,13 +485,20 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
     complete = max_levels is None or max_levels >= eng.max_depth
     masks = eng.root_level() if depth > 0 else eng.empty((0, eng.W), torch.int64)
     total = 0
+    inherit = _inherit_on() and eng.has_walk_vertex
+    parent = None
     for lvl in range(depth):
         n = masks.shape[0]
         if n == 0:
             break
         t0 = time.perf_counter()
         k_act = lvl + 1
-        status = _eval_level(eng, masks, k_act, dist, rank, world)
+        last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
+        # witnesses: the rows active at the vertex that certified a candidate; the next level inherits them
+        wit = torch.zeros((n, eng.W), dtype=torch.int64, device=eng.tdev) \
+            if (inherit and not last and n >= WITNESS_MIN_LEVEL) else None
+        status = _eval_level(eng, masks, k_act, dist, rank, world, wit, parent)
+        parent = None
         # one device reduction answers "is any candidate flagged at all" for the three report bits (a sync per question
         # is what the small levels and the sharded runs pay for)
         any_flag = int((status & (ST_NUMERIC | ST_THIN | ST_BORDER)).max().item()) if n else 0
@@ -492,7 +543,6 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
             after = torch.stack([((status & ST_REGION) != 0).sum(), (status & (ST_THIN | ST_BORDER)).max().to(torch.int64)]).cpu()
             n_reg = int(after[0])
             any_flag |= int(after[1])
-        last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
         if last:
             # no next level: only the count is needed, not the ordered index list
             feas_idx = None
@@ -506,7 +556,10 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
             statuses.append((masks.cpu().numpy(), status.cpu().numpy()))
         if digest:
             sums.append((n, _checksum(status)))
-        nxt = eng.children(masks, feas_idx, k_act, dist if world > 1 else None) if not last else eng.empty((0, eng.W), torch.int64)
+        keep = {} if wit is not None else None
+        nxt = eng.children(masks, feas_idx, k_act, dist if world > 1 else None, keep) if not last else eng.empty((0, eng.W), torch.int64)
+        if keep:
+            parent = ParentLevel(keep['feas_masks'], keep['ws'], keep['nf'], wit[feas_idx].contiguous())
         torch.cuda.synchronize(eng.tdev)
         total += n
         stats.append(dict(level=lvl + 1, candidates=n, feasible=n_feas, optimal=n_opt, regions=n_reg,
