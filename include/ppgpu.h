@@ -85,14 +85,16 @@ int ppgpu_level_eval(ppgpu_program* prog, const uint64_t* d_masks, int64_t n, in
 
 /* ppgpu_level_eval with feasibility WITNESSES (no reference counterpart: the reference solves one LP per candidate,
  * mplp_program.py:411-444, and shares nothing between candidates or levels).
- *   d_witness      (n x words uint64, zero-initialised by the caller, or NULL) receives, for every candidate certified by
- *                  the vertex walk or by inheritance, the mask of ALL rows active at the certifying vertex;
+ *   d_witness      (n x PPGPU_WITNESS_SLOTS x words uint64, zero-initialised by the caller, or NULL) receives, for every
+ *                  candidate certified by the vertex walk or by inheritance, the mask of ALL rows active at the certifying
+ *                  vertex (slot 0) and at a later vertex of the walk that holds the candidate too (slot 1, may stay 0);
  *   d_parent_*     (or NULL / 0) describe the level the candidates were generated from: the feasible masks and the
  *                  workspace exactly as ppgpu_children_count / ppgpu_children_prepare left them (the workspace holds the
  *                  hash set of those masks), and the witnesses of those parents in the same order.  A candidate one of
  *                  whose parents has a witness that also holds the added row is certified by that same vertex before any
  *                  LP work is spent on it (and passes the witness on).
  * Decisions are identical with and without witnesses; only which kernel exhibits the feasible point changes. */
+#define PPGPU_WITNESS_SLOTS 2
 int ppgpu_level_eval_w(ppgpu_program* prog, const uint64_t* d_masks, int64_t n, int32_t k_act, uint8_t* d_status,
                        int32_t stages, uint64_t* d_witness, const uint64_t* d_parent_feas, int64_t parent_nf,
                        const void* d_parent_ws, const uint64_t* d_parent_wit, ppgpu_stream stream);

@@ -16,6 +16,7 @@ COUNTER_NAMES = ('k1_candidates', 'k2_lps', 'k2_pivots', 'k2_work', 'k4_lps', 'k
 # status bits (csrc/tolerances.h)
 ST_RANK, ST_FEAS, ST_OPT, ST_REGION, ST_BORDER, ST_NUMERIC, ST_THIN = 1, 2, 4, 8, 16, 32, 64
 OPT_K2W_MIN = 0   # ppgpu_set_option (include/ppgpu.h)
+WITNESS_SLOTS = 2  # PPGPU_WITNESS_SLOTS
 
 
 class Dims(ctypes.Structure):

@@ -248,9 +248,10 @@ static cudaError_t ensure_warm(ppgpu_program* p, long long cap, cudaStream_t st)
     return cudaSuccess;
 }
 
+static_assert(PPGPU_WITNESS_SLOTS == PPG_WITNESS_SLOTS, "witness slots: include/ppgpu.h and csrc/tolerances.h disagree");
 // what ppgpu_level_eval_w adds to a level evaluation (all optional)
 struct WitnessIo {
-    uint64_t* out = nullptr;                 // n x W: witness of every candidate the walk certifies / that inherits one
+    uint64_t* out = nullptr;                 // n x slots x W: witnesses of the candidates the walk certifies / that inherit one
     const uint64_t* parent_feas = nullptr;   // parent level: feasible masks (nf x W), K6 workspace with their hash set,
     long long parent_nf = 0;                 // and the witnesses of those parents in the same order
     const void* parent_ws = nullptr;
@@ -353,7 +354,7 @@ int ppgpu_level_eval_w(ppgpu_program* p, const uint64_t* d_masks, int64_t n, int
     const long long chunk = walk ? walk_chunk() : level_chunk();
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t nn = n - off < chunk ? n - off : chunk;
-        wio.out = d_witness ? d_witness + (size_t)off * p->dev.W : nullptr;
+        wio.out = d_witness ? d_witness + (size_t)off * PPGPU_WITNESS_SLOTS * p->dev.W : nullptr;
         const int rc = level_eval_chunk(p, d_masks + (size_t)off * p->dev.W, nn, k_act, d_status + off, stages,
                                         (cudaStream_t)stream, wio);
         if (rc) return rc;

@@ -44,12 +44,13 @@ struct K2wCtx {
     int* bvar;        // nb         row id basic in dictionary row i
     int* nvar;        // nf         row id nonbasic in column j
     int* where;       // R0         >= 0: dictionary row, < 0: ~column
-    uint64_t* orig;   // R0 x W4    segment: bit b of row a = candidate P+{a,b} exists in the segment
+    uint64_t* orig;   // R0 x W4    segment: bit b >= a of row a = candidate P+{a,b} exists in the segment; bit a of row b (the
+                      //             unused half) = ... and it passed the rank screen (only those may ever be certified)
     uint64_t* todo;   // R0 x W4    ... and is still open; symmetric (see k2w_mark_row)
     int* rowstart;    // R0         position in the segment of the first candidate with second-last row a
     uint64_t* nbm;    // W4         bitmask of the nonbasic rows
     int* fixrow;      // K2W_MAXFIX rows of the prefix currently fixed, in order
-    uint64_t* witness; // n x Wm (global, may be null): nonbasic-row mask of the vertex that certified a candidate
+    uint64_t* witness; // n x PPG_WITNESS_SLOTS x Wm (global, may be null): nonbasic-row masks of vertices that hold a candidate
     int nb, nf, ld, lds, R0, W4, Wm;
 };
 
@@ -489,12 +490,18 @@ struct K2wRegDict {
     }
 };
 
+// bits of word w with index >= a
+__device__ __forceinline__ uint64_t k2w_ge_mask(int a, int w) {
+    const int aw = a >> 6;
+    return w < aw ? 0ull : (w == aw ? (~0ull << (a & 63)) : ~0ull);
+}
+
 // certify candidate (a, b) of the segment (the caller has cleared its todo bit)
 __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int a, int b) {
     int rank = 0;
     const int w = b >> 6;
-    for (int w2 = 0; w2 < w; ++w2) rank += __popcll(c.orig[(size_t)a * c.W4 + w2]);
-    rank += __popcll(c.orig[(size_t)a * c.W4 + w] & ((1ull << (b & 63)) - 1ull));
+    for (int w2 = 0; w2 < w; ++w2) rank += __popcll(c.orig[(size_t)a * c.W4 + w2] & k2w_ge_mask(a, w2));
+    rank += __popcll(c.orig[(size_t)a * c.W4 + w] & k2w_ge_mask(a, w) & ((1ull << (b & 63)) - 1ull));
     const long long idx = seg_base + c.rowstart[a] + rank;
     // fire-and-forget OR on the aligned word that holds the byte (a load + store would stall the walker for an L2 round trip)
     const uintptr_t addr = reinterpret_cast<uintptr_t>(status + idx);
@@ -502,13 +509,51 @@ __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict
     // the WITNESS: the rows active at the certifying vertex.  Every superset of the candidate inside this mask is certified
     // by the same vertex - the next level inherits it (k6_children.cu::inherit_kernel) instead of walking again
     if (c.witness)
-        for (int w = 0; w < c.Wm; ++w) c.witness[idx * c.Wm + w] = c.nbm[w];
+        for (int w = 0; w < c.Wm; ++w) c.witness[idx * (PPG_WITNESS_SLOTS * c.Wm) + w] = c.nbm[w];
 }
 
-// bits of word w with index >= a
-__device__ __forceinline__ uint64_t k2w_ge_mask(int a, int w) {
-    const int aw = a >> 6;
-    return w < aw ? 0ull : (w == aw ? (~0ull << (a & 63)) : ~0ull);
+// second witness slot of candidate (a, b), a < b, which is closed already: the vertex the walk is at holds it as well.
+// Two different vertices per parent cover more children than one (CPU model, level 4 -> 5 of the 100x30x6 program: 76 % of
+// the children inherit from first witnesses alone, 88 % with a later vertex next to them)
+__device__ __forceinline__ void k2w_second_witness(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int a, int b) {
+    int rank = 0;
+    const int w = b >> 6;
+    for (int w2 = 0; w2 < w; ++w2) rank += __popcll(c.orig[(size_t)a * c.W4 + w2] & k2w_ge_mask(a, w2));
+    rank += __popcll(c.orig[(size_t)a * c.W4 + w] & k2w_ge_mask(a, w) & ((1ull << (b & 63)) - 1ull));
+    const long long idx = seg_base + c.rowstart[a] + rank;
+    for (int x = 0; x < c.Wm; ++x) c.witness[idx * (PPG_WITNESS_SLOTS * c.Wm) + c.Wm + x] = c.nbm[x];
+    // (a candidate the walk gave up on earlier is closed too: this vertex certifies it after all)
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(status + idx);
+    atomicOr(reinterpret_cast<unsigned*>(addr & ~(uintptr_t)3), (unsigned)PPG_ST_FEAS << (8u * (unsigned)(addr & 3)));
+}
+
+// after a pivot that made row r nonbasic (and after k2w_mark_row): every CLOSED candidate {r, y} of the segment with y
+// nonbasic is revisited; lanes over y
+__device__ __forceinline__ void k2w_revisit_row(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int r, int lane) {
+    for (int y = lane; y < c.R0; y += 32) {
+        if (y == r || !((c.nbm[y >> 6] >> (y & 63)) & 1ull)) continue;
+        const int a = y < r ? y : r, b = y < r ? r : y;
+        const uint64_t bit = 1ull << (b & 63);
+        if (!(c.orig[(size_t)a * c.W4 + (b >> 6)] & bit) || (c.todo[(size_t)a * c.W4 + (b >> 6)] & bit)) continue;
+        if (!((c.orig[(size_t)b * c.W4 + (a >> 6)] >> (a & 63)) & 1ull)) continue;   // failed the rank screen
+        k2w_second_witness(c, status, seg_base, a, b);
+    }
+}
+
+// the same for every closed candidate at the first vertex of a segment (the prefix has just been fixed); lanes over a
+__device__ __forceinline__ void k2w_revisit_all(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int lane) {
+    for (int a = lane; a < c.R0; a += 32) {
+        if (!((c.nbm[a >> 6] >> (a & 63)) & 1ull)) continue;
+        for (int w = 0; w < c.W4; ++w) {
+            uint64_t bits = c.nbm[w] & c.orig[(size_t)a * c.W4 + w] & ~c.todo[(size_t)a * c.W4 + w] & k2w_ge_mask(a + 1, w);
+            while (bits) {
+                const int bb = w * 64 + __ffsll((long long)bits) - 1;
+                bits &= bits - 1ull;
+                if (!((c.orig[(size_t)bb * c.W4 + (a >> 6)] >> (a & 63)) & 1ull)) continue;   // failed the rank screen
+                k2w_second_witness(c, status, seg_base, a, bb);
+            }
+        }
+    }
 }
 
 // Open candidates live in a SYMMETRIC bit matrix: bit y of row x is set while the candidate with last rows {x, y} is open
@@ -677,6 +722,8 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     const uint8_t sb = status[q];
                     open = (sb & PPG_ST_RANK) && !(sb & PPG_ST_FEAS);
                     atomicOr(reinterpret_cast<unsigned long long*>(c.orig + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
+                    if ((sb & PPG_ST_RANK) && a1 != b1)
+                        atomicOr(reinterpret_cast<unsigned long long*>(c.orig + (size_t)b1 * W4 + (a1 >> 6)), 1ull << (a1 & 63));
                     if (open) {
                         atomicOr(reinterpret_cast<unsigned long long*>(c.todo + (size_t)a1 * W4 + (b1 >> 6)), 1ull << (b1 & 63));
                         if (a1 != b1) atomicOr(reinterpret_cast<unsigned long long*>(c.todo + (size_t)b1 * W4 + (a1 >> 6)), 1ull << (a1 & 63));
@@ -721,6 +768,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     } else {
                         n_cert += k2w_mark_all(c, status, i, lane);
                         __syncwarp();
+                        if (c.witness && k_act >= 2) k2w_revisit_all(c, status, i, lane);
                         stage = 1; a = -1;
                     }
                 }
@@ -788,7 +836,10 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     vertex_ok = dict.pivot(c, l, j, lane);
                     ++npiv;
                     if (!vertex_ok) break;
-                    if (stage != 0) n_cert += k2w_mark_row(c, status, i, rl, lane);
+                    if (stage != 0) {
+                        n_cert += k2w_mark_row(c, status, i, rl, lane);
+                        if (c.witness && k_act >= 2) k2w_revisit_row(c, status, i, rl, lane);
+                    }
                     __syncwarp();
                 }
                 if (!vertex_ok) {

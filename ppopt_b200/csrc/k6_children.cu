@@ -390,7 +390,7 @@ cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, cons
 // 76 % of the level-5 candidates are certified by one of their five parents' witnesses, which removes them - the ones that
 // are easy to reach - from the walk.  Parents are found in the open-addressing hash set K6 built when it generated this
 // level (children_prepare: table slots -> index into the parent level's feasible list); parent_wit is the witness array
-// gathered in that order.  One thread per candidate; rows are dropped from the highest down (measured: the middle
+// gathered in that order (PPG_WITNESS_SLOTS masks per parent: the certifying vertex and a later vertex of the walk).  One thread per candidate; rows are dropped from the highest down (measured: the middle
 // positions inherit most often, the first one least).  An inherited witness is passed on (witness_out), so that
 // certificates propagate down the levels without any further pivot.
 __device__ __forceinline__ int hash_find(const uint64_t* __restrict__ feas, int W, const int* __restrict__ table,
@@ -435,21 +435,25 @@ inherit_kernel(int W, const uint64_t* __restrict__ masks, long long n, uint8_t* 
                         ++lookups;
                         const int e = hash_find(pfeas, W, table, cap_mask, sub);
                         if (e < 0) continue;   // (cannot happen for a child K6 let through: every parent is feasible)
-                        // the parent's witness holds the parent (or is empty: certified by the relaxation / the simplex)
-                        bool inside = true;
-                        uint64_t wv[MAXW];
+                        // a parent's witnesses hold the parent (or are empty: certified by the relaxation / the simplex)
 #pragma unroll
-                        for (int x = 0; x < MAXW; ++x) {
-                            wv[x] = x < W ? __ldg(pwit + (long long)e * W + x) : 0ull;
-                            if (m.w[x] & ~wv[x]) inside = false;
-                        }
-                        if (inside) {
-                            got = 1;
-                            status[i] = sb | PPG_ST_FEAS;
-                            if (witness_out)
+                        for (int sl = 0; sl < PPG_WITNESS_SLOTS; ++sl) {
+                            if (got) continue;
+                            bool inside = true;
+                            uint64_t wv[MAXW];
 #pragma unroll
-                                for (int x = 0; x < MAXW; ++x)
-                                    if (x < W) witness_out[i * W + x] = wv[x];
+                            for (int x = 0; x < MAXW; ++x) {
+                                wv[x] = x < W ? __ldg(pwit + ((long long)e * PPG_WITNESS_SLOTS + sl) * W + x) : 0ull;
+                                if (m.w[x] & ~wv[x]) inside = false;
+                            }
+                            if (inside) {
+                                got = 1;
+                                status[i] = sb | PPG_ST_FEAS;
+                                if (witness_out)
+#pragma unroll
+                                    for (int x = 0; x < MAXW; ++x)
+                                        if (x < W) witness_out[i * (PPG_WITNESS_SLOTS * W) + x] = wv[x];
+                            }
                         }
                     }
                 }

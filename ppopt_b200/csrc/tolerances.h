@@ -50,6 +50,10 @@
 #define PPG_ST_THIN 64u     // full-dimension decision taken inside PPG_RADIUS_BAND of the 1e-8 threshold (reported)
 #define PPG_ST_PRE 128u       // transient: passed the K3 thread-per-candidate prefilter (cleared by k34_kernel)
 
+// witness slots per candidate (ppgpu_level_eval_w): [0] the vertex that certified it (walk or inheritance), [1] a later
+// vertex of the walk that holds it as well
+#define PPG_WITNESS_SLOTS 2
+
 // LP return codes
 #define PPG_LP_OPTIMAL 0
 #define PPG_LP_EARLY 1

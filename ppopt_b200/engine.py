@@ -104,8 +104,8 @@ class Engine:
     def level_eval(self, masks: torch.Tensor, k_act: int, status: Optional[torch.Tensor] = None, stages: int = 7,
                    lo: int = 0, hi: Optional[int] = None, witness: Optional[torch.Tensor] = None,
                    parent: Optional['ParentLevel'] = None) -> torch.Tensor:
-        """status bytes of masks[lo:hi].  ``witness`` (n x W int64, zeros): receives the active-row mask of the vertex
-        that certified a candidate; ``parent``: the level the candidates were generated from (feasible masks, their hash
+        """status bytes of masks[lo:hi].  ``witness`` (n x WITNESS_SLOTS x W int64, zeros): receives the active-row masks of
+        vertices that hold a candidate; ``parent``: the level the candidates were generated from (feasible masks, their hash
         set, their witnesses) - candidates covered by a parent's witness are certified without any LP work
         (ppgpu_level_eval_w)."""
         n = masks.shape[0]
@@ -121,7 +121,7 @@ class Engine:
                     if parent is not None else (None, 0, None, None)
                 _lib.check(self.lib.ppgpu_level_eval_w(self.h, masks.data_ptr() + lo * self.W * 8, hi - lo, k_act,
                                                        status.data_ptr() + lo, stages,
-                                                       None if witness is None else witness.data_ptr() + lo * self.W * 8,
+                                                       None if witness is None else witness.data_ptr() + lo * _lib.WITNESS_SLOTS * self.W * 8,
                                                        pf, pnf, pws, pw, self._stream()), 'level_eval_w')
         return status
 
@@ -404,7 +404,7 @@ def _eval_level(eng: Engine, masks: torch.Tensor, k_act: int, dist, rank: int, w
             eng.level_eval(masks, k_act, status, 7, lo, hi, witness=wit, parent=parent)
         else:
             packed = torch.cat([masks[lo:hi] for lo, hi in mine])
-            wp = torch.zeros_like(packed) if wit is not None else None
+            wp = torch.zeros((packed.shape[0],) + tuple(wit.shape[1:]), dtype=torch.int64, device=eng.tdev) if wit is not None else None
             st = eng.level_eval(packed, k_act, None, 7, witness=wp, parent=parent)
             off = 0
             for lo, hi in mine:
@@ -495,7 +495,7 @@ def solve(program, max_levels: Optional[int] = None, collect_status: bool = Fals
         k_act = lvl + 1
         last = lvl + 1 == eng.max_depth or (lvl + 1 == depth and not expand_last)
         # witnesses: the rows active at the vertex that certified a candidate; the next level inherits them
-        wit = torch.zeros((n, eng.W), dtype=torch.int64, device=eng.tdev) \
+        wit = torch.zeros((n, _lib.WITNESS_SLOTS, eng.W), dtype=torch.int64, device=eng.tdev) \
             if (inherit and not last and n >= WITNESS_MIN_LEVEL) else None
         status = _eval_level(eng, masks, k_act, dist, rank, world, wit, parent)
         parent = None

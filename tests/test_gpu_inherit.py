@@ -31,13 +31,13 @@ def _engine(name):
 def _levels(engine, eng, depth, witnesses):
     """level loop through the C ABI; returns [(masks, status, witness)]"""
     import torch
-    from ppopt_b200._lib import ST_FEAS
+    from ppopt_b200._lib import ST_FEAS, WITNESS_SLOTS
     masks, parent, out = eng.root_level(), None, []
     for lvl in range(depth):
         n = masks.shape[0]
         if n == 0:
             break
-        wit = torch.zeros((n, eng.W), dtype=torch.int64, device=eng.tdev) if witnesses else None
+        wit = torch.zeros((n, WITNESS_SLOTS, eng.W), dtype=torch.int64, device=eng.tdev) if witnesses else None
         st = eng.level_eval(masks, lvl + 1, witness=wit, parent=parent)
         out.append((masks, st, wit))
         if lvl + 1 == depth:
@@ -73,10 +73,12 @@ def test_inheritance_never_changes_a_decision(name):
         if f'level{lv}_status' in g and len(g[f'level{lv}_status']) == s1.shape[0]:
             assert numpy.array_equal(s1.cpu().numpy() & 3, g[f'level{lv}_status'] & 3), f'{name} level {lv + 1}'
         # a witness holds its candidate
-        has = (w1 != 0).any(dim=1)
-        assert bool(((m1 & ~w1) == 0).all(dim=1)[has].all()), f'{name} level {lv + 1}: witness does not contain its candidate'
-        # ... and belongs to a candidate that is feasible
-        assert bool(((s1[has] & 2) != 0).all())
+        for sl in range(w1.shape[1]):
+            ws = w1[:, sl]
+            has = (ws != 0).any(dim=1)
+            assert bool(((m1 & ~ws) == 0).all(dim=1)[has].all()), f'{name} level {lv + 1}: witness does not contain its candidate'
+            # ... and belongs to a candidate that is feasible
+            assert bool(((s1[has] & 2) != 0).all())
     eng.close()
     if name in ('synthetic_30_6_40_s0', 'rand_wide_40_8_90_s5'):
         assert c1['inherited'] - c0['inherited'] > 0, 'nothing was inherited'
