@@ -77,8 +77,10 @@ def test_inheritance_never_changes_a_decision(name):
             ws = w1[:, sl]
             has = (ws != 0).any(dim=1)
             assert bool(((m1 & ~ws) == 0).all(dim=1)[has].all()), f'{name} level {lv + 1}: witness does not contain its candidate'
-            # ... and belongs to a candidate that is feasible
-            assert bool(((s1[has] & 2) != 0).all())
+            # ... and the first slot belongs to a candidate certified feasible (the second may also sit on a candidate the walk
+            # gave up on earlier: it is only ever used if the relaxation / the simplex call that candidate feasible)
+            if sl == 0:
+                assert bool(((s1[has] & 2) != 0).all())
     eng.close()
     if name in ('synthetic_30_6_40_s0', 'rand_wide_40_8_90_s5'):
         assert c1['inherited'] - c0['inherited'] > 0, 'nothing was inherited'
