@@ -515,13 +515,14 @@ __device__ __forceinline__ void k2w_certify(const K2wCtx& c, uint8_t* __restrict
 // second witness slot of candidate (a, b), a < b, which is closed already: the vertex the walk is at holds it as well.
 // Two different vertices per parent cover more children than one (CPU model, level 4 -> 5 of the 100x30x6 program: 76 % of
 // the children inherit from first witnesses alone, 88 % with a later vertex next to them)
-__device__ __forceinline__ void k2w_second_witness(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int a, int b) {
+__device__ __forceinline__ void k2w_second_witness(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int a, int b, int turn) {
     int rank = 0;
     const int w = b >> 6;
     for (int w2 = 0; w2 < w; ++w2) rank += __popcll(c.orig[(size_t)a * c.W4 + w2] & k2w_ge_mask(a, w2));
     rank += __popcll(c.orig[(size_t)a * c.W4 + w] & k2w_ge_mask(a, w) & ((1ull << (b & 63)) - 1ull));
     const long long idx = seg_base + c.rowstart[a] + rank;
-    for (int x = 0; x < c.Wm; ++x) c.witness[idx * (PPG_WITNESS_SLOTS * c.Wm) + c.Wm + x] = c.nbm[x];
+    const int slot = 1 + (turn % (PPG_WITNESS_SLOTS - 1));
+    for (int x = 0; x < c.Wm; ++x) c.witness[idx * (PPG_WITNESS_SLOTS * c.Wm) + slot * c.Wm + x] = c.nbm[x];
     // (a candidate the walk gave up on earlier is closed too; its feasible bit is left to the relaxation / the simplex, and
     // its witness is only ever used if they set it: the next level looks at the witnesses of FEASIBLE parents)
     (void)status;
@@ -531,14 +532,14 @@ __device__ __forceinline__ void k2w_second_witness(const K2wCtx& c, uint8_t* __r
 // nonbasic is revisited; lanes over y.  (Measured on the bench program: revisiting only one block of 32 rows y per pivot
 // makes level 4 cheaper but leaves older second witnesses - 81.5 % of level 5 inherit instead of 85.5 %, the step is 8 ms
 // slower.)
-__device__ __forceinline__ void k2w_revisit_row(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int r, int lane) {
+__device__ __forceinline__ void k2w_revisit_row(const K2wCtx& c, uint8_t* __restrict__ status, long long seg_base, int r, int lane, int turn) {
     for (int y = lane; y < c.R0; y += 32) {
         if (y == r || !((c.nbm[y >> 6] >> (y & 63)) & 1ull)) continue;
         const int a = y < r ? y : r, b = y < r ? r : y;
         const uint64_t bit = 1ull << (b & 63);
         if (!(c.orig[(size_t)a * c.W4 + (b >> 6)] & bit) || (c.todo[(size_t)a * c.W4 + (b >> 6)] & bit)) continue;
         if (!((c.orig[(size_t)b * c.W4 + (a >> 6)] >> (a & 63)) & 1ull)) continue;   // failed the rank screen
-        k2w_second_witness(c, status, seg_base, a, b);
+        k2w_second_witness(c, status, seg_base, a, b, turn);
     }
 }
 
@@ -552,7 +553,7 @@ __device__ __forceinline__ void k2w_revisit_all(const K2wCtx& c, uint8_t* __rest
                 const int bb = w * 64 + __ffsll((long long)bits) - 1;
                 bits &= bits - 1ull;
                 if (!((c.orig[(size_t)bb * c.W4 + (a >> 6)] >> (a & 63)) & 1ull)) continue;   // failed the rank screen
-                k2w_second_witness(c, status, seg_base, a, bb);
+                k2w_second_witness(c, status, seg_base, a, bb, 0);
             }
         }
     }
@@ -840,7 +841,7 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
                     if (!vertex_ok) break;
                     if (stage != 0) {
                         n_cert += k2w_mark_row(c, status, i, rl, lane);
-                        if (c.witness && k_act >= 2) k2w_revisit_row(c, status, i, rl, lane);
+                        if (c.witness && k_act >= 2) k2w_revisit_row(c, status, i, rl, lane, npiv);
                     }
                     __syncwarp();
                 }

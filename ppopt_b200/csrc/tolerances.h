@@ -50,8 +50,9 @@
 #define PPG_ST_THIN 64u     // full-dimension decision taken inside PPG_RADIUS_BAND of the 1e-8 threshold (reported)
 #define PPG_ST_PRE 128u       // transient: passed the K3 thread-per-candidate prefilter (cleared by k34_kernel)
 
-// witness slots per candidate (ppgpu_level_eval_w): [0] the vertex that certified it (walk or inheritance), [1] a later
-// vertex of the walk that holds it as well
+// witness slots per candidate (ppgpu_level_eval_w): [0] the vertex that certified it (walk or inheritance), [1..] later
+// vertices of the walk that hold it as well, written in turn.  Measured on the bench program (share of level 5 that inherits /
+// ms per step): 1 slot 73 % / 240.7, 2 slots 85.5 % / 223.9, 3 slots 87.3 % / 220.3 - two it is (16 B per slot and candidate)
 #define PPG_WITNESS_SLOTS 2
 
 // LP return codes
