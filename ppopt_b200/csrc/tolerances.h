@@ -52,7 +52,9 @@
 
 // witness slots per candidate (ppgpu_level_eval_w): [0] the vertex that certified it (walk or inheritance), [1..] later
 // vertices of the walk that hold it as well, written in turn.  Measured on the bench program (share of level 5 that inherits /
-// ms per step): 1 slot 73 % / 240.7, 2 slots 85.5 % / 223.9, 3 slots 87.3 % / 220.3 - two it is (16 B per slot and candidate)
+// ms per step): 1 slot 73 % / 240.7, 2 slots 85.5 % / 223.9, 3 slots 87.3 % / 220.3 - two it is (16 B per slot and candidate).  Also measured and rejected: slot 1 as the UNION of all
+// later vertices (a "cover": certifies as well, but names no vertex a child could pass on - 82 % / 239.8; as a third slot
+// next to two vertices 85.6 % / 230.5)
 #define PPG_WITNESS_SLOTS 2
 
 // LP return codes
