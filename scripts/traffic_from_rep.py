@@ -23,7 +23,7 @@ rd, ru = get('dram__bytes_read.sum')
 wr, wu = get('dram__bytes_write.sum')
 rd, wr = rd * scale[ru], wr * scale[wu]
 d = {'dram_bytes_per_launch': int(rd + wr), 'dram_read': int(rd), 'dram_write': int(wr), 'candidates_per_launch': ncand,
-     'kernel': vals[hdr.index('Kernel Name')][:120], 'duration_us_under_ncu': get('gpu__time_duration.sum')[0], 'source': note}
+     'kernel': vals[hdr.index('Kernel Name')][:120], 'duration_ms_under_ncu': get('gpu__time_duration.sum')[0], 'source': note}
 try:
     d['smem_wavefronts_pct_of_peak'] = get('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed')[0]
 except ValueError:
