@@ -35,6 +35,8 @@ struct ppgpu_program {
     double* d_warm_resid = nullptr;
     long long* d_warm_idx = nullptr;
     unsigned long long* d_warm_count = nullptr;
+    int* d_k2w_order = nullptr;   // scratch for the cost order of the walk's work items (grown on demand)
+    size_t k2w_order_cap = 0;
     long long k2w_min = 100000;   // smallest launch the vertex walk (K2w) is used for (ppgpu_set_option)
     double prof_ms[PPGPU_NUM_FAMILIES] = {0};
     long long prof_launches[PPGPU_NUM_FAMILIES] = {0};
@@ -149,6 +151,7 @@ int ppgpu_program_create(const ppgpu_dims* d, const double* A, const double* b, 
 int ppgpu_program_destroy(ppgpu_program* p) {
     if (!p) return 0;
     for (void* d : p->allocs) cudaFree(d);
+    if (p->d_k2w_order) cudaFree(p->d_k2w_order);
     warm_release(p);
     for (auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
@@ -291,9 +294,18 @@ static int level_eval_chunk(ppgpu_program* p, const uint64_t* d_masks, int64_t n
         // certificates shared between the candidates of a prefix (vertex walk); the relaxation only sees what is left
         ProfScope ps(p, st, 8);
         bool handled = false;
-        e = launch_k2w(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st, &handled, wio.out);
+        const size_t want = k2w_order_scratch_ints(walk_chunk());   // one allocation per handle, sized for the largest launch
+        if (want > p->k2w_order_cap) {
+            // (earlier launches may still read the old buffer)
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail("K2w order scratch", e);
+            if (p->d_k2w_order) cudaFree(p->d_k2w_order);
+            p->d_k2w_order = nullptr; p->k2w_order_cap = 0;
+            if ((e = cudaMalloc((void**)&p->d_k2w_order, want * sizeof(int))) != cudaSuccess) return fail("K2w order scratch", e);
+            p->k2w_order_cap = want;
+        }
+        e = launch_k2w(p->dev, d_masks, n, k_act, d_status, next_queue(p, st), p->d_counters, p->sm_count, st, &handled, wio.out, p->d_k2w_order);
         if (e != cudaSuccess) return fail("K2w vertex walk", e);
-        if (handled) p->launches++;
+        if (handled) p->launches += (n > 128ll * 8 * p->sm_count) ? 4 : 1;   // + the three kernels that order the work items
     }
     if ((stages & 2) && !(stages & 8)) {
         // feasibility certificates first (cheap); the simplex only sees what is left, and starts from K2a's last iterate

@@ -629,7 +629,8 @@ template <class Dict>
 __global__ void __launch_bounds__(256, 1)
 k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, int k_act, uint8_t* __restrict__ status,
                 unsigned long long* __restrict__ queue, unsigned long long* __restrict__ counters, int chunk,
-                int walker_bytes, int lds, int W4, int group_items, int split_len, uint64_t* __restrict__ witness) {
+                int walker_bytes, int lds, int W4, int group_items, int split_len, uint64_t* __restrict__ witness,
+                const int* __restrict__ order, long long items) {
     extern __shared__ unsigned char k2w_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int RPL = Dict::RPL;
@@ -679,10 +680,16 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
         return limit;
     };
     for (;;) {
+        // work items are handed out most-open-candidates-first (k2w_order_items below): the cost of an item is its number
+        // of open candidates, not its length, and an expensive item picked last is the tail of the launch
         unsigned long long v = 0;
-        if (lane == 0) v = atomicAdd(queue, (unsigned long long)chunk);
-        const long long c0 = (long long)__shfl_sync(PPG_FULL, v, 0);
-        if (c0 >= n) break;
+        if (lane == 0) {
+            v = atomicAdd(queue, 1ull);
+            if (v < (unsigned long long)items && order) v = (unsigned long long)order[v];
+        }
+        const long long item = (long long)__shfl_sync(PPG_FULL, v, 0);
+        if (item >= items) break;
+        const long long c0 = item * chunk;
         const long long c1 = (c0 + chunk < n) ? c0 + chunk : n;
         // Ownership.  Work items are ranges of `chunk` candidates; a range boundary x that falls inside a prefix is moved to
         // cut(x): to the end of that prefix when less than `split` candidates of it lie beyond x (short prefixes stay whole:
@@ -889,11 +896,69 @@ k2w_walk_kernel(DevProgram P, const uint64_t* __restrict__ masks, long long n, i
     }
 }
 
+// ---- longest-processing-time-first order of the work items: cost = open candidates (rank OK, not yet certified) in the item's
+// range, counting sort into K2W_COST_BUCKETS descending buckets (the order inside a bucket does not matter)
+constexpr int K2W_COST_BUCKETS = 1025;
+
+__global__ void __launch_bounds__(256) k2w_item_cost_kernel(const uint8_t* __restrict__ status, long long n, int chunk, long long items,
+                                                            int* __restrict__ cost, int* __restrict__ hist) {
+    const int lane = threadIdx.x & 31;
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= items) return;
+    const long long c0 = item * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
+    int cnt = 0;
+    for (long long q = c0 + lane; q < c1; q += 32) {
+        const uint8_t sb = status[q];
+        cnt += ((sb & PPG_ST_RANK) && !(sb & PPG_ST_FEAS)) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(PPG_FULL, cnt);
+    if (cnt > K2W_COST_BUCKETS - 1) cnt = K2W_COST_BUCKETS - 1;
+    if (lane == 0) { cost[item] = cnt; atomicAdd(&hist[K2W_COST_BUCKETS - 1 - cnt], 1); }
+}
+
+// exclusive scan of the histogram in place (one block)
+__global__ void __launch_bounds__(1024) k2w_item_scan_kernel(int* __restrict__ hist) {
+    __shared__ int sh[K2W_COST_BUCKETS + 1];
+    for (int i = threadIdx.x; i < K2W_COST_BUCKETS; i += blockDim.x) sh[i] = hist[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < K2W_COST_BUCKETS; ++i) { const int c = sh[i]; sh[i] = run; run += c; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K2W_COST_BUCKETS; i += blockDim.x) hist[i] = sh[i];
+}
+
+__global__ void __launch_bounds__(256) k2w_item_scatter_kernel(const int* __restrict__ cost, long long items, int* __restrict__ offs,
+                                                               int* __restrict__ order) {
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= items) return;
+    const int pos = atomicAdd(&offs[K2W_COST_BUCKETS - 1 - cost[item]], 1);
+    order[pos] = (int)item;
+}
+
+// scratch: cost (items) | order (items) | hist (K2W_COST_BUCKETS)  ints
+size_t k2w_order_scratch_ints(long long n) { return (size_t)(2 * (n / 128 + 2) + K2W_COST_BUCKETS); }
+
+static cudaError_t k2w_order_items(const uint8_t* status, long long n, int chunk, long long items, int* scratch, cudaStream_t st,
+                                   const int** order_out) {
+    int* cost = scratch;
+    int* order = scratch + items;
+    int* hist = scratch + 2 * items;
+    cudaError_t e = cudaMemsetAsync(hist, 0, K2W_COST_BUCKETS * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k2w_item_cost_kernel<<<(unsigned)((items * 32 + 255) / 256), 256, 0, st>>>(status, n, chunk, items, cost, hist);
+    k2w_item_scan_kernel<<<1, 1024, 0, st>>>(hist);
+    k2w_item_scatter_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(cost, items, hist, order);
+    *order_out = order;
+    return cudaGetLastError();
+}
+
 #define K2W_COMMA ,
 template <class Dict>
 static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                                 unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st,
-                                bool* handled, uint64_t* witness) {
+                                bool* handled, uint64_t* witness, int* order_scratch) {
     const int nb = P.wk_nb, ld = P.wk_ld, lds = ld | 1, W4 = (P.R0 + 63) / 64;
     size_t wb = k2w_dict_smem_bytes<Dict>(nb, lds) + (size_t)lds * 8 + (size_t)2 * P.R0 * W4 * 8 + (size_t)W4 * 8 +
                 (size_t)(nb + P.nfree + 2 * P.R0 + K2W_MAXFIX + 2) * 4;
@@ -929,8 +994,14 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
     static const int groups_env = getenv("PPGPU_K2W_GROUPS") ? atoi(getenv("PPGPU_K2W_GROUPS")) : -1;
     static const int split_len = getenv("PPGPU_K2W_SPLIT") ? atoi(getenv("PPGPU_K2W_SPLIT")) : 2048;
     const int group_items = groups_env >= 0 ? groups_env : (n / walkers < 16384 ? 1 : 0);
+    const long long items = (n + chunk - 1) / chunk;
+    const int* order = nullptr;
+    static const int lpt_on = getenv("PPGPU_K2W_LPT") ? atoi(getenv("PPGPU_K2W_LPT")) : 1;
+    if (lpt_on && order_scratch && items > walkers && items < (1ll << 30)) {
+        if ((e = k2w_order_items(status, n, (int)chunk, items, order_scratch, st, &order)) != cudaSuccess) return e;
+    }
     kern<<<(unsigned)grid, 32 * wpc, smem, st>>>(P, masks, n, k_act, status, queue, counters, (int)chunk, (int)wb, lds, W4,
-                                                 group_items, split_len, witness);
+                                                 group_items, split_len, witness, order, items);
     *handled = true;
     return cudaGetLastError();
 }
@@ -938,13 +1009,13 @@ static cudaError_t launch_k2w_t(const DevProgram& P, const uint64_t* masks, long
 // *handled == false: the walk is off for this program / level (no vertex dictionary, prefix too long, dictionary too large)
 cudaError_t launch_k2w(const DevProgram& P, const uint64_t* masks, long long n, int k_act, uint8_t* status,
                        unsigned long long* queue, unsigned long long* counters, int sm_count, cudaStream_t st, bool* handled,
-                       uint64_t* witness) {
+                       uint64_t* witness, int* order_scratch) {
     *handled = false;
     static const int on = getenv("PPGPU_K2W") ? atoi(getenv("PPGPU_K2W")) : 1;
     static const int regs_on = getenv("PPGPU_K2W_REG") ? atoi(getenv("PPGPU_K2W_REG")) : 0;
     if (!on || !P.wk_ok || k_act < 1 || k_act - 2 > K2W_MAXFIX || P.W > 4 || P.nfree > 64) return cudaSuccess;
     const int rpl = (P.wk_nb + 31) / 32;
-#define K2W_GO(D) return launch_k2w_t<D>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled, witness)
+#define K2W_GO(D) return launch_k2w_t<D>(P, masks, n, k_act, status, queue, counters, sm_count, st, handled, witness, order_scratch)
     // The register-resident dictionary (instantiated for the 100 x 30 x 6 bench program: 76 basic rows x 37 columns) is
     // an EXPERIMENT, off by default (PPGPU_K2W_REG=1): 255 registers + 2 KB of spills, measured 2.6x slower per pivot than
     // the shared-memory dictionary (1395 vs 535 ms on levels 4-5); kept because it decides identically and is the
