@@ -236,6 +236,11 @@ class Engine:
         eq = list(range(self.n_eq))
         m = masks_np.view(numpy.uint64).reshape(-1, self.W)
         bits = numpy.unpackbits(m.view(numpy.uint8).reshape(m.shape[0], -1), axis=1, bitorder='little')
+        per_row = bits.sum(1)
+        if m.shape[0] and (per_row == per_row[0]).all():
+            # one level: every set has the same cardinality - one nonzero for all of them
+            cols = (numpy.nonzero(bits)[1] + self.n_eq).reshape(m.shape[0], int(per_row[0])).tolist()
+            return [eq + c for c in cols] if eq else cols
         return [eq + (numpy.nonzero(r)[0] + self.n_eq).tolist() for r in bits]
 
 
@@ -276,6 +281,48 @@ def _to_host(x):
     return numpy.asarray(x)
 
 
+# Kept-index lists of every region of a level (mpqp_utils.py:181-195): of the R0 rows of a region, rows [0, k_act) are the
+# multiplier rows (lambda_set: the constraint they belong to), [k_act, k_act + n_inact) the inactive constraints
+# (regular_set: position, constraint), the rest the Theta rows (omega_set).  Returns, for the kept rows of all regions in
+# row-major order: val (the index each list reports), pos (row - k_act: the "position" of regular_set), and cnt (3 x ns:
+# kept rows per region, of which multiplier rows, of which multiplier + inactive rows).  Two statements of the same
+# arithmetic: whole-array numpy for host buffers, whole-array torch for device buffers (5,570 regions x 112 rows at the
+# bench workload: on the host this was the largest part of the region assembly).
+def _kept_index_lists_numpy(kept_all, asets, k_act, n_inact, ne, m):
+    ns = kept_all.shape[0]
+    ri, ci = numpy.nonzero(kept_all)
+    is_l, is_r = ci < k_act, (ci >= k_act) & (ci < k_act + n_inact)
+    val = ci - (k_act + n_inact)
+    if k_act > 0:
+        val = numpy.where(is_l, asets[ri, numpy.minimum(ne + ci, ne + k_act - 1)], val)
+    if n_inact > 0:
+        act_bool = numpy.zeros((ns, m), dtype=bool)
+        if asets.shape[1]:
+            act_bool[numpy.arange(ns)[:, None], asets] = True
+        inactive = numpy.nonzero(~act_bool)[1].reshape(ns, n_inact)
+        val = numpy.where(is_r, inactive[ri, numpy.clip(ci - k_act, 0, n_inact - 1)], val)
+    cnt = numpy.stack([kept_all.sum(1), kept_all[:, :k_act].sum(1), kept_all[:, :k_act + n_inact].sum(1)]).astype(numpy.int64)
+    return val.astype(numpy.int64), (ci - k_act).astype(numpy.int64), cnt
+
+
+def _kept_index_lists_torch(kept_all, asets, k_act, n_inact, ne, m):
+    ns = kept_all.shape[0]
+    nz = torch.nonzero(kept_all)                     # row-major, like numpy.nonzero
+    ri, ci = nz[:, 0], nz[:, 1]
+    val = ci - (k_act + n_inact)
+    if k_act > 0:
+        val = torch.where(ci < k_act, asets[ri, torch.clamp(ne + ci, max=ne + k_act - 1)], val)
+    if n_inact > 0:
+        act_bool = torch.zeros((ns, m), dtype=torch.bool, device=kept_all.device)
+        if asets.shape[1]:
+            act_bool.scatter_(1, asets, True)
+        inactive = torch.nonzero(~act_bool)[:, 1].reshape(ns, n_inact)
+        is_r = (ci >= k_act) & (ci < k_act + n_inact)
+        val = torch.where(is_r, inactive[ri, torch.clamp(ci - k_act, 0, n_inact - 1)], val)
+    cnt = torch.stack([kept_all.sum(1), kept_all[:, :k_act].sum(1), kept_all[:, :k_act + n_inact].sum(1)])
+    return val, ci - k_act, cnt
+
+
 def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, info, d2h: Optional[list] = None) -> list:
     """CriticalRegion objects from K5's buffers (field meaning: mpqp_utils.py:181-195).  The buffers may be device tensors
     (the solver's case) or numpy arrays.  Everything that can be done for the whole level at once is done on whole arrays -
@@ -307,41 +354,37 @@ def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, in
         # kept, de-duplicated half-spaces of every region, stacked; a region's block is a contiguous slice of it
         E_cat, f_cat = host(rows[:, :, 1:][nodup_all]), host(rows[:, :, :1][nodup_all])
         e_off = numpy.concatenate([[0], numpy.cumsum(host(nodup_all.sum(1)))]).tolist()
-    kept_all = host(kept_all)
     asets = numpy.asarray(active_sets, dtype=numpy.int64).reshape(ns, ne + k_act)
     aset_lists = asets.tolist()
-    # kept-index lists of every region: rows [0, k_act) are the multiplier rows (lambda_set: the constraint they belong to),
-    # [k_act, k_act + n_inact) the inactive constraints (regular_set: position, constraint), the rest the Theta rows (omega_set)
-    ri, ci = numpy.nonzero(kept_all)
-    bounds = numpy.searchsorted(ri, numpy.arange(ns + 1)).tolist()
-    is_l, is_r = ci < k_act, (ci >= k_act) & (ci < k_act + n_inact)
-    val = numpy.empty(ci.shape[0], dtype=numpy.int64)
-    val[is_l] = asets[ri[is_l], ne + ci[is_l]]
-    act_bool = numpy.zeros((ns, m), dtype=bool)
-    if asets.shape[1]:
-        act_bool[numpy.arange(ns)[:, None], asets] = True
-    if n_inact > 0:
-        inactive = numpy.nonzero(~act_bool)[1].reshape(ns, n_inact)
-        val[is_r] = inactive[ri[is_r], ci[is_r] - k_act]
-    val[~(is_l | is_r)] = ci[~(is_l | is_r)] - (k_act + n_inact)
-    n_l = numpy.searchsorted(ri[is_l], numpy.arange(ns + 1))
-    n_lr = numpy.searchsorted(ri[is_l | is_r], numpy.arange(ns + 1))
-    n_l, n_lr = (n_l[1:] - n_l[:-1]).tolist(), (n_lr[1:] - n_lr[:-1]).tolist()
-    val_list, pos_list = val.tolist(), (ci - k_act).tolist()
-    out = []
-    for si in range(ns):
-        if not emitted[si]:
-            out.append(None)
-            continue
+    if on_dev:
+        val, pos, cnt = _kept_index_lists_torch(kept_all, torch.from_numpy(asets).to(kept_all.device), k_act, n_inact, ne, m)
+        val, pos, cnt = host(val), host(pos), host(cnt)
+    else:
+        val, pos, cnt = _kept_index_lists_numpy(numpy.asarray(kept_all), asets, k_act, n_inact, ne, m)
+    bounds = numpy.concatenate([[0], numpy.cumsum(cnt[0])]).tolist()
+    n_l, n_lr = cnt[1].tolist(), cnt[2].tolist()
+    val_list, pos_list = val.tolist(), pos.tolist()
+    # per region only views and list slices remain; the views of a whole array come from ONE iteration over its first axis
+    # (list(array)), not from ns index operations
+    import gc
+    gc_was_on = gc.isenabled()
+    gc.disable()       # thousands of small objects in one go: a generation-2 collection in the middle costs more than the assembly
+    try:
+        lo_l, hi_l = bounds[:-1], bounds[1:]
+        le_l = [lo + x for lo, x in zip(lo_l, n_l)]
+        re_l = [lo + x for lo, x in zip(lo_l, n_lr)]
         if t == 1:
-            E = numpy.array([[1], [-1]])
-            f = numpy.array([[info[si, 3]], [-info[si, 2]]])
+            E_l = [numpy.array([[1], [-1]]) for _ in range(ns)]
+            f_l = [numpy.array([[hi_], [-lo_]]) for lo_, hi_ in zip(info[:, 2].tolist(), info[:, 3].tolist())]
         else:
-            E, f = E_cat[e_off[si]:e_off[si + 1]], f_cat[e_off[si]:e_off[si + 1]]
-        lo = bounds[si]
-        l_end, r_end, hi = lo + n_l[si], lo + n_lr[si], bounds[si + 1]
-        out.append(cr_cls(A_all[si], b_all[si], C_all[si], d_all[si], E, f, aset_lists[si], val_list[r_end:hi],
-                          val_list[lo:l_end], [pos_list[l_end:r_end], val_list[l_end:r_end]]))
+            E_l = [E_cat[a:b] for a, b in zip(e_off[:-1], e_off[1:])]
+            f_l = [f_cat[a:b] for a, b in zip(e_off[:-1], e_off[1:])]
+        out = [cr_cls(A, b, C, d, E, f, aset, val_list[re:hi], val_list[lo:le], [pos_list[le:re], val_list[le:re]]) if em else None
+               for A, b, C, d, E, f, aset, lo, le, re, hi, em in zip(list(A_all), list(b_all), list(C_all), list(d_all), E_l, f_l,
+                                                                     aset_lists, lo_l, le_l, re_l, hi_l, emitted)]
+    finally:
+        if gc_was_on:
+            gc.enable()
     if d2h is not None:
         d2h.append(copied if on_dev else 0)
     return out

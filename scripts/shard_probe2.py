@@ -31,6 +31,11 @@ def run(ranges):
 run([(0, n // 64)])
 whole = run([(0, n)])
 print('env', {k: v for k, v in os.environ.items() if k.startswith('PPGPU_K2W')}, 'whole level', whole, '-> ideal k2w per rank %.1f' % (whole['k2w_walk'] / G))
-for r in ranks:
-    ch = sharding.chunks(n, r, G)
-    print(f'rank {r}: {len(ch)} chunks of {ch[0][1] - ch[0][0]}', run(ch))
+for per_rank in [int(x) for x in os.environ.get('PROBE_CHUNKS', '16').split(',')]:
+    sharding.CHUNKS_PER_RANK = per_rank
+    rows = []
+    for r in ranks:
+        ch = sharding.chunks(n, r, G)
+        rows.append(run(ch))
+    print(f'chunks per rank {per_rank} ({len(ch)} x {ch[0][1] - ch[0][0]}):', ' | '.join(
+        f"r{r} k2w {x['k2w_walk']} k34 {x['k34_kkt_cheb']} sum {round(sum(x.values()), 1)}" for r, x in zip(ranks, rows)))

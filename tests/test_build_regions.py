@@ -72,3 +72,36 @@ def test_region_assembly_skips_non_regions_and_handles_empty_input():
     info[1, 0] = -1.0   # singular KKT system
     assert engine.build_regions(eng, CriticalRegion, [[0, 1]] * 3, 2, laws, rows, flags, info) == [None, None, None]
     assert engine.build_regions(eng, CriticalRegion, [], 2, laws[:0], rows[:0], flags[:0], info[:0]) == []
+
+
+@pytest.mark.parametrize('name', ['synthetic_30_6_40_s0', 'mpc_n5', 'transport_mplp', 'doc_portfolio'])
+def test_tensor_buffers_assemble_like_numpy_buffers(name):
+    """engine.build_regions has a whole-array numpy statement (host buffers) and a whole-array torch statement (device
+    buffers: the solver's case) of the kept-index arithmetic and of the half-space gather; fed the same buffers - as CPU
+    tensors here - they must build identical regions"""
+    import torch
+    from twin_binding import Twin
+    from ppopt_b200 import engine
+    from ppopt_b200.critical_region import CriticalRegion
+    path = os.path.join(GOLDEN, name + '.npz')
+    g = numpy.load(path)
+    tw = Twin.from_npz(path)
+    eng = types.SimpleNamespace(n=tw.n, t=tw.t, n_eq=tw.n_eq, m=tw.m, mi=tw.m - tw.n_eq)
+    by_k = {}
+    for r in golden_regions(g)[:200]:
+        by_k.setdefault(len(r['active_set']) - tw.n_eq, []).append(r)
+    for k_act, regs in by_k.items():
+        bufs = [tw.emit(tw.masks([r['active_set'].tolist()])[0], margins=True) for r in regs]
+        laws, rows, flags, info = (numpy.stack([b[i] for b in bufs]) for i in (1, 2, 3, 4))
+        asets = [r['active_set'].tolist() for r in regs]
+        a = engine.build_regions(eng, CriticalRegion, asets, k_act, laws, rows, flags, info)
+        b = engine.build_regions(eng, CriticalRegion, asets, k_act, *[torch.from_numpy(x.copy()) for x in (laws, rows, flags, info)])
+        assert len(a) == len(b) == len(regs)
+        for x, y in zip(a, b):
+            assert (x is None) == (y is None)
+            if x is None:
+                continue
+            for fld in 'AbCdEf':
+                assert numpy.array_equal(getattr(x, fld), getattr(y, fld)), (name, x.active_set, fld)
+            assert (x.active_set, x.omega_set, x.lambda_set, x.regular_set) == (y.active_set, y.omega_set, y.lambda_set, y.regular_set)
+            assert all(type(v) is int for lst in (y.omega_set, y.lambda_set, y.regular_set[0], y.regular_set[1]) for v in lst)
