@@ -288,6 +288,14 @@ def _to_host(x):
 # kept rows per region, of which multiplier rows, of which multiplier + inactive rows).  Two statements of the same
 # arithmetic: whole-array numpy for host buffers, whole-array torch for device buffers (5,570 regions x 112 rows at the
 # bench workload: on the host this was the largest part of the region assembly).
+# Measured on the B200 box (bench e2e, 5,570 regions per solve): with the torch statement on the device AND the collector
+# paused the end-to-end step went from 268 to 331 ms although both are 2-3x faster on CPU tensors in isolation; both are
+# therefore off by default (PPGPU_ASSEMBLY_DEVICE=1 / PPGPU_ASSEMBLY_PAUSE_GC=1 switch them on), the whole-array numpy
+# statement runs on the host copy of the flags.
+_INDEX_LISTS_ON_DEVICE = __import__('os').environ.get('PPGPU_ASSEMBLY_DEVICE', '0') == '1'
+_PAUSE_GC = __import__('os').environ.get('PPGPU_ASSEMBLY_PAUSE_GC', '0') == '1'
+
+
 def _kept_index_lists_numpy(kept_all, asets, k_act, n_inact, ne, m):
     ns = kept_all.shape[0]
     ri, ci = numpy.nonzero(kept_all)
@@ -356,19 +364,20 @@ def build_regions(eng: Engine, cr_cls, active_sets, k_act, laws, rows, flags, in
         e_off = numpy.concatenate([[0], numpy.cumsum(host(nodup_all.sum(1)))]).tolist()
     asets = numpy.asarray(active_sets, dtype=numpy.int64).reshape(ns, ne + k_act)
     aset_lists = asets.tolist()
-    if on_dev:
+    if on_dev and _INDEX_LISTS_ON_DEVICE:
         val, pos, cnt = _kept_index_lists_torch(kept_all, torch.from_numpy(asets).to(kept_all.device), k_act, n_inact, ne, m)
         val, pos, cnt = host(val), host(pos), host(cnt)
     else:
-        val, pos, cnt = _kept_index_lists_numpy(numpy.asarray(kept_all), asets, k_act, n_inact, ne, m)
+        val, pos, cnt = _kept_index_lists_numpy(host(kept_all) if on_dev else numpy.asarray(kept_all), asets, k_act, n_inact, ne, m)
     bounds = numpy.concatenate([[0], numpy.cumsum(cnt[0])]).tolist()
     n_l, n_lr = cnt[1].tolist(), cnt[2].tolist()
     val_list, pos_list = val.tolist(), pos.tolist()
     # per region only views and list slices remain; the views of a whole array come from ONE iteration over its first axis
     # (list(array)), not from ns index operations
     import gc
-    gc_was_on = gc.isenabled()
-    gc.disable()       # thousands of small objects in one go: a generation-2 collection in the middle costs more than the assembly
+    gc_was_on = gc.isenabled() and _PAUSE_GC
+    if gc_was_on:
+        gc.disable()   # thousands of small objects in one go: a generation-2 collection in the middle costs more than the assembly
     try:
         lo_l, hi_l = bounds[:-1], bounds[1:]
         le_l = [lo + x for lo, x in zip(lo_l, n_l)]
