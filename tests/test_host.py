@@ -154,6 +154,47 @@ for lv in range(int(g['n_levels'])):
     bits_in[mine] |= 8
     st3 = sharding.gather_region_bits(bits_in, mine, dist)
     assert numpy.array_equal(st3.numpy() & 8, full.numpy() & 8)
+# ---- witnesses under sharding (engine._eval_level): a rank evaluates its chunks packed into one array, scatters status
+# bytes AND witness words back, both are all-reduced (disjoint supports); every rank must end with exactly what the two
+# ranks produced for their own chunks.  A stand-in engine (CPU checker: status bytes, sequential walk with witnesses) plays
+# the kernels; MIN_CHUNK is lowered so that a rank owns several chunks of these small levels.
+from ppopt_b200 import engine, _lib
+sharding.MIN_CHUNK, sharding.CHUNKS_PER_RANK = 4, 3
+W4 = (tw.R0 + 63) // 64
+class FakeEngine:
+    tdev = torch.device('cpu'); W = tw.W
+    def level_eval(self, masks, k_act, status=None, stages=7, lo=0, hi=None, witness=None, parent=None):
+        n = masks.shape[0]; hi = n if hi is None else hi
+        if status is None: status = torch.zeros((n,), dtype=torch.uint8)
+        m = masks[lo:hi].numpy()
+        status[lo:hi] = torch.from_numpy(tw.eval(m.view(numpy.uint64)))
+        if witness is not None and hi > lo and k_act >= 1:
+            cert, _, wit = tw.k2w_witness(m.view(numpy.uint64))
+            witness[lo:hi, 0, :] = torch.from_numpy(wit[:, :tw.W].astype(numpy.int64))
+        return status
+fake = FakeEngine()
+for lv in range(int(g['n_levels'])):
+    cands = g[f'level{lv}_candidates']; n = len(cands)
+    if n < 16:
+        continue
+    masks = torch.from_numpy(tw.masks(cands.tolist()).view(numpy.int64).reshape(n, tw.W))
+    k_act = cands.shape[1] - tw.n_eq
+    wit = torch.zeros((n, _lib.WITNESS_SLOTS, tw.W), dtype=torch.int64)
+    st = engine._eval_level(fake, masks, k_act, dist, rank, world, wit, None)
+    assert numpy.array_equal(st.numpy() & 11, g[f'level{lv}_status'] & 11), (rank, lv)
+    want = torch.zeros_like(wit)
+    for r in range(world):
+        ch = sharding.chunks(n, r, world)
+        assert len(ch) > 1
+        packed = torch.cat([masks[lo:hi] for lo, hi in ch])
+        wp = torch.zeros((packed.shape[0], _lib.WITNESS_SLOTS, tw.W), dtype=torch.int64)
+        fake.level_eval(packed, k_act, None, 7, witness=wp)
+        off = 0
+        for lo, hi in ch:
+            want[lo:hi] = wp[off:off + hi - lo]; off += hi - lo
+    assert torch.equal(wit, want), (rank, lv)
+    has = (wit[:, 0] != 0).any(dim=1)
+    assert bool(((masks & ~wit[:, 0]) == 0).all(dim=1)[has].all()) and int(has.sum()) > 0, (rank, lv)
 dist.barrier(); dist.destroy_process_group()
 print('ok', rank)
 '''
@@ -162,7 +203,8 @@ print('ok', rank)
 def test_level_sharding_world_size_2_gloo(tmp_path):
     """N>1 host path on CPU: each rank evaluates its chunks (CPU checker standing in for the kernels), status bytes
     are all-reduced over gloo, every rank ends with the reference's full status vector; the region payloads of the
-    owning ranks are gathered as raw buffers (sharding.gather_regions) and the region bits made global."""
+    owning ranks are gathered as raw buffers (sharding.gather_regions) and the region bits made global; witnesses written
+    by a rank for its packed chunks are scattered back and all-reduced like the status bytes (engine._eval_level)."""
     script = tmp_path / 'worker.py'
     script.write_text(WORKER)
     port = str(29500 + os.getpid() % 2000)
