@@ -820,8 +820,12 @@ struct WalkDict {
 // witness (n x W4 words, optional): the mask of ALL rows nonbasic at the vertex that certified candidate i - what the kernel
 // leaves for the next level (k6_children.cu::inherit_kernel: a child one of whose parents has a witness holding the added
 // row too is certified by that same vertex).  W4 = ceil(R0 / 64).
+// slots >= 2: slot 1 receives a LATER vertex of the walk that holds an already closed candidate as well (the kernel's
+// k2w_revisit_row / k2w_revisit_all: after a pivot that brought row r in, every closed candidate {r, y} with y nonbasic;
+// after the prefix has been fixed, every closed candidate with both rows nonbasic).  closed (optional, n flags): candidates
+// that arrive certified (by inheritance): part of the segment, never a target, revisited like the others.
 long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std::vector<char>& certified,
-                    uint64_t* witness = nullptr) {
+                    uint64_t* witness = nullptr, int slots = 1, const uint8_t* closed = nullptr) {
     certified.assign(n, 0);
     if (!P.wk_ok || n == 0) return 0;
     std::vector<std::vector<int>> acts(n);
@@ -838,26 +842,39 @@ long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std:
         long s1 = i + 1;
         while (s1 < n && std::equal(acts[i].begin(), acts[i].begin() + p, acts[s1].begin())) ++s1;
         // open candidates of the segment: (a, b) -> index
-        std::vector<std::vector<long>> open(P.R0, std::vector<long>(P.R0, -1));
+        std::vector<std::vector<long>> open(P.R0, std::vector<long>(P.R0, -1)), orig;
         for (long q = i; q < s1; ++q) {
             const int b = acts[q][k - 1], a = k >= 2 ? acts[q][k - 2] : b;
             open[a][b] = q;
         }
+        orig = open;
+        if (closed)
+            for (long q = i; q < s1; ++q)
+                if (closed[q]) open[k >= 2 ? acts[q][k - 2] : acts[q][k - 1]][acts[q][k - 1]] = -1;
+        const int W4 = (P.R0 + 63) / 64;
+        bool second_on = true;   // off while k2w_mark_all is restated: it writes first witnesses only
+        auto write_witness = [&](long q, int slot) {
+            uint64_t* wq = witness + ((size_t)q * slots + slot) * W4;
+            for (int w = 0; w < W4; ++w) wq[w] = 0;
+            for (int j = 0; j < wd.nf; ++j) wq[wd.nvar[j] >> 6] |= 1ull << (wd.nvar[j] & 63);
+        };
         auto mark_row = [&](int r) {
             for (int y = 0; y < P.R0; ++y) {
                 if (!wd.nonbasic(y)) continue;
                 const int a = std::min(r, y), b = std::max(r, y);
                 if (open[a][b] >= 0) {
                     certified[open[a][b]] = 1;
-                    if (witness) {
-                        const int W4 = (P.R0 + 63) / 64;
-                        uint64_t* wq = witness + (size_t)W4 * open[a][b];
-                        for (int w = 0; w < W4; ++w) wq[w] = 0;
-                        for (int j = 0; j < wd.nf; ++j) wq[wd.nvar[j] >> 6] |= 1ull << (wd.nvar[j] & 63);
-                    }
+                    if (witness) write_witness(open[a][b], 0);
                     open[a][b] = -1;
                 }
+                if (witness && second_on && slots >= 2 && k >= 2 && y != r && orig[a][b] >= 0 && open[a][b] < 0) write_witness(orig[a][b], 1);
             }
+        };
+        auto revisit_all = [&]() {
+            if (!witness || slots < 2 || k < 2) return;
+            for (int a = 0; a < P.R0; ++a)
+                for (int b = a + 1; b < P.R0; ++b)
+                    if (wd.nonbasic(a) && wd.nonbasic(b) && orig[a][b] >= 0 && open[a][b] < 0) write_witness(orig[a][b], 1);
         };
         bool restart = wd.pivots > 3000 || !wd.ok;
         auto fix_prefix = [&]() -> bool {
@@ -874,7 +891,9 @@ long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std:
             return true;
         };
         if (fix_prefix()) {
-            for (int r = 0; r < P.R0; ++r) if (wd.nonbasic(r)) mark_row(r);
+            // (the kernel's k2w_mark_all writes first witnesses only; second ones come from k2w_revisit_all right after it)
+            { second_on = false; for (int r = 0; r < P.R0; ++r) if (wd.nonbasic(r)) mark_row(r); second_on = true; }
+            revisit_all();
             for (int a = 0; a < P.R0 && wd.ok; ++a) {
                 bool any = false;
                 for (int b = a; b < P.R0; ++b) any = any || open[a][b] >= 0;
@@ -882,7 +901,8 @@ long k2w_walk_level(const ReducedProgram& P, const uint64_t* masks, long n, std:
                 if (wd.pivots > 3000) {
                     restart = true;
                     if (!fix_prefix()) break;
-                    for (int r = 0; r < P.R0; ++r) if (wd.nonbasic(r)) mark_row(r);
+                    { second_on = false; for (int r = 0; r < P.R0; ++r) if (wd.nonbasic(r)) mark_row(r); second_on = true; }
+                    revisit_all();
                 }
                 std::vector<char> fc(wd.nf, 0);
                 for (int r : fixed_rows) fc[~wd.where[r]] = 1;
@@ -998,10 +1018,12 @@ long twin_k2w(void* h, const uint64_t* masks, long ncand, uint8_t* certified) {
     for (long i = 0; i < ncand; ++i) certified[i] = (uint8_t)c[i];
     return piv;
 }
-// ... with the witnesses (ncand x ceil(R0 / 64) words, zero where the walk certified nothing)
-long twin_k2w_witness(void* h, const uint64_t* masks, long ncand, uint8_t* certified, uint64_t* witness) {
+// ... with the witnesses (ncand x slots x ceil(R0 / 64) words, zero where there is none); closed: optional flags of candidates
+// that arrive certified (inherited)
+long twin_k2w_witness(void* h, const uint64_t* masks, long ncand, uint8_t* certified, uint64_t* witness, int slots,
+                      const uint8_t* closed) {
     std::vector<char> c;
-    const long piv = k2w_walk_level(((Twin*)h)->P, masks, ncand, c, witness);
+    const long piv = k2w_walk_level(((Twin*)h)->P, masks, ncand, c, witness, slots < 1 ? 1 : slots, closed);
     for (long i = 0; i < ncand; ++i) certified[i] = (uint8_t)c[i];
     return piv;
 }

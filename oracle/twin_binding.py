@@ -136,17 +136,23 @@ class Twin:
         piv = l.twin_k2w(self.h, masks.ctypes.data, masks.shape[0], cert.ctypes.data)
         return cert, int(piv)
 
-    def k2w_witness(self, masks):
-        """sequential K2w with witnesses: (certified flags, pivots, witness masks n x ceil(R0 / 64) uint64) - the witness of a
-        certified candidate is the set of all rows active at the certifying vertex"""
+    def k2w_witness(self, masks, slots=1, closed=None):
+        """sequential K2w with witnesses: (certified flags, pivots, witness masks).  The witness of a certified candidate is
+        the set of all rows active at the certifying vertex; with slots >= 2, slot 1 holds a later vertex of the walk that
+        holds the candidate as well (the kernel's revisits).  slots == 1: witness is n x ceil(R0 / 64) uint64, else
+        n x slots x ceil(R0 / 64).  closed: optional flags of candidates that arrive certified (inherited) - part of their
+        segment, never a target of the walk, revisited like the others."""
         l = lib()
-        l.twin_k2w_witness.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]
+        l.twin_k2w_witness.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_void_p]
         l.twin_k2w_witness.restype = ctypes.c_long
         masks = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(-1, self.W)
         cert = numpy.zeros(masks.shape[0], dtype=numpy.uint8)
-        wit = numpy.zeros((masks.shape[0], (self.R0 + 63) // 64), dtype=numpy.uint64)
-        piv = l.twin_k2w_witness(self.h, masks.ctypes.data, masks.shape[0], cert.ctypes.data, wit.ctypes.data)
-        return cert, int(piv), wit
+        wit = numpy.zeros((masks.shape[0], slots, (self.R0 + 63) // 64), dtype=numpy.uint64)
+        cl = None if closed is None else numpy.ascontiguousarray(closed, dtype=numpy.uint8)
+        piv = l.twin_k2w_witness(self.h, masks.ctypes.data, masks.shape[0], cert.ctypes.data, wit.ctypes.data, slots,
+                                 None if cl is None else cl.ctypes.data)
+        return cert, int(piv), (wit[:, 0] if slots == 1 else wit)
 
     def pivots(self):
         return lib().twin_pivots(self.h)

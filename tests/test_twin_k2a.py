@@ -133,7 +133,8 @@ def test_walk_certificates_are_sound(name):
 @pytest.mark.parametrize('name', golden_names())
 def test_witnesses_are_feasible_vertices_and_inheritance_is_sound(name):
     """What the next level inherits (ppgpu_level_eval_w, k6_children.cu::inherit_kernel), restated on the CPU: the witness of
-    a certified candidate is the active-row set of the certifying vertex.  Checked with numpy, independently of the walk:
+    a certified candidate is the active-row set of the certifying vertex (slot 0) or of a later vertex of the walk that holds
+    the candidate as well (slot 1).  Checked with numpy, independently of the walk:
     the witness contains its candidate, its rows determine a point z, and z satisfies every row of the feasibility system.
     And the inheritance rule against the UNMODIFIED reference's verdicts: every golden candidate of the next level that
     lies inside the witness of one of its parents (and passes the rank screen) is feasible for the reference."""
@@ -151,35 +152,42 @@ def test_witnesses_are_feasible_vertices_and_inheritance_is_sound(name):
     checked = inherited = 0
     for lv in range(int(g['n_levels']) - 1):
         c, c2, st2 = g[f'level{lv}_candidates'], g[f'level{lv + 1}_candidates'], g[f'level{lv + 1}_status']
+        st = g[f'level{lv}_status']
         if len(c) == 0 or len(c2) == 0 or c.shape[1] - n_eq > 32 or c.shape[1] - n_eq < 1 or len(c) > 20000:
             continue
         masks = tw.masks(c.tolist())
-        cert, _, wit = tw.k2w_witness(masks)
+        cert, _, wit2 = tw.k2w_witness(masks, slots=2)
+        wit = numpy.ascontiguousarray(wit2[:, 0])
         m64 = numpy.ascontiguousarray(masks).view(numpy.uint64).reshape(len(c), -1)
         has = cert.astype(bool)
-        assert numpy.all((wit[~has] == 0))
-        assert numpy.all((m64[has] & ~wit[has, :m64.shape[1]]) == 0), f'{name}: a witness does not contain its candidate'
+        assert numpy.all((wit2[~has, 0] == 0))   # (slot 1 may also sit on a candidate the walk gave up on: still a vertex that holds it)
         bits = numpy.unpackbits(wit.view(numpy.uint8), axis=1, bitorder='little')[:, :G.shape[0]].astype(bool)
         seen = set()
-        for i in numpy.nonzero(has)[0][:400]:
-            key = wit[i].tobytes()
-            if key in seen:
-                continue
-            seen.add(key)
-            rows = numpy.nonzero(bits[i])[0]
-            assert len(rows) == G.shape[1], f'{name}: a witness is not a basis'
-            z = numpy.linalg.solve(G[rows], h[rows])
-            assert numpy.max(G @ z - h) <= 1e-7 * scale, f'{name}: the witness vertex violates a row'
-            checked += 1
+        for sl in range(2):
+            ws = numpy.ascontiguousarray(wit2[:, sl])
+            hs = (ws != 0).any(axis=1)
+            assert numpy.all((m64[hs] & ~ws[hs, :m64.shape[1]]) == 0), f'{name}: a witness does not contain its candidate'
+            bs = numpy.unpackbits(ws.view(numpy.uint8), axis=1, bitorder='little')[:, :G.shape[0]].astype(bool)
+            for i in numpy.nonzero(hs)[0][:400]:
+                key = ws[i].tobytes()
+                if key in seen:
+                    continue
+                seen.add(key)
+                rows = numpy.nonzero(bs[i])[0]
+                assert len(rows) == G.shape[1], f'{name}: a witness is not a basis'
+                z = numpy.linalg.solve(G[rows], h[rows])
+                assert numpy.max(G @ z - h) <= 1e-7 * scale, f'{name}: the witness vertex violates a row'
+                checked += 1
+        bits2 = numpy.unpackbits(numpy.ascontiguousarray(wit2[:, 1]).view(numpy.uint8), axis=1, bitorder='little')[:, :G.shape[0]].astype(bool)
         # inheritance: child = parent + one row, inside the parent's witness
         by_set = {tuple(r): i for i, r in enumerate(c.tolist())}
         for child, s2 in zip(c2.tolist(), st2.tolist()):
             for drop in range(n_eq, len(child)):
                 par = tuple(child[:drop] + child[drop + 1:])
                 i = by_set.get(par)
-                if i is None or not has[i]:
+                if i is None or (st[i] & 3) != 3:     # the engine only looks at the witnesses of FEASIBLE parents
                     continue
-                if bits[i, child[drop] - n_eq]:
+                if bits[i, child[drop] - n_eq] or bits2[i, child[drop] - n_eq]:
                     inherited += 1
                     if s2 & 1:
                         assert s2 & 2, f'{name}: {child} inherits a certificate but the reference calls it infeasible'
