@@ -384,13 +384,14 @@ cudaError_t children_write(const DevProgram& P, const uint64_t* feas_masks, cons
 
 // ---- certificates inherited from the previous level ------------------------------------------------------------------------
 // The vertex walk (k2w_walk.cu) leaves, for every candidate it certifies, the WITNESS: the mask of all rows active at the
-// certifying vertex (~n' rows, the candidate's own among them).  A candidate C of the next level is feasible as soon as the
-// witness of ONE of its parents C \ {b} also has row b active: the same vertex, the same exact statement ("the rows of C
-// are nonbasic at a vertex whose basic slacks are >= -1e-8").  Measured on the 100x30x6 program (CPU model of the walk):
-// 76 % of the level-5 candidates are certified by one of their five parents' witnesses, which removes them - the ones that
-// are easy to reach - from the walk.  Parents are found in the open-addressing hash set K6 built when it generated this
-// level (children_prepare: table slots -> index into the parent level's feasible list); parent_wit is the witness array
-// gathered in that order (PPG_WITNESS_SLOTS masks per parent: the certifying vertex and a later vertex of the walk).  One thread per candidate; rows are dropped from the highest down (measured: the middle
+// certifying vertex (~n' rows, the candidate's own among them), and next to it the mask of a later vertex of the walk that
+// holds the candidate as well (PPG_WITNESS_SLOTS masks per candidate).  A candidate C of the next level is feasible as soon
+// as a witness of ONE of its parents C \ {b} also has row b active: the same vertex, the same exact statement ("the rows of
+// C are nonbasic at a vertex whose basic slacks are >= -1e-8").  On the 100x30x6 program 85 % of the candidates of levels
+// 4-5 are certified this way (CPU model scripts/witness_coverage_model.py: 84 % / 86 %), which removes them - the ones
+// that are easy to reach - from the walk.  Parents are found in the open-addressing hash set K6 built when it generated
+// this level (children_prepare: table slots -> index into the parent level's feasible list); parent_wit is the witness
+// array gathered in that order.  One thread per candidate; rows are dropped from the highest down (CPU model: the middle
 // positions inherit most often, the first one least).  An inherited witness is passed on (witness_out), so that
 // certificates propagate down the levels without any further pivot.
 __device__ __forceinline__ int hash_find(const uint64_t* __restrict__ feas, int W, const int* __restrict__ table,
